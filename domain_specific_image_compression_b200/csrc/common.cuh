@@ -1,0 +1,85 @@
+// Shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "sic.h"
+
+namespace sic {
+
+void set_error(const char *fmt, ...);
+
+#define SIC_CHECK_ARG(cond, ...)         \
+    do {                                 \
+        if (!(cond)) {                   \
+            sic::set_error(__VA_ARGS__); \
+            return SIC_E_BADARG;         \
+        }                                \
+    } while (0)
+
+#define SIC_CHECK_LAUNCH(name)                                                        \
+    do {                                                                              \
+        cudaError_t e_ = cudaGetLastError();                                          \
+        if (e_ != cudaSuccess) {                                                      \
+            sic::set_error("%s: launch failed: %s", name, cudaGetErrorString(e_));    \
+            return (int)e_;                                                           \
+        }                                                                             \
+    } while (0)
+
+constexpr float kLog2e = 1.44269504088896340736f;   // distributions.py:6 rounded to fp32
+constexpr float kSigmaMin = 1e-3f, kSigmaMax = 1e3f;  // distributions.py:23,43
+constexpr float kNuMin = 2.0f, kNuMax = 100.0f;       // distributions.py:24
+
+__device__ __forceinline__ float clamp_keep_nan(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// streaming 128-bit accesses: activations are touched once, keep them out of L1
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(float4 *p, const float4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter = (c0,c1,c2,c3), key = (k0,k1)
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// 23 random bits -> odd multiple of 2^-24 in (-1/2, 1/2): symmetric, never exactly +-1/2, every step exact in fp32
+__device__ __forceinline__ float u32_to_noise(uint32_t r) { return ((float)(r >> 9) + 0.5f) * 1.1920928955078125e-07f - 0.5f; }
+
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace sic

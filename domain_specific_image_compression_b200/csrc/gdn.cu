@@ -1,0 +1,324 @@
+// K2: GDN / IGDN with diagonal gamma — forward (bit-exact replay of the eager op sequence) and backward.
+//
+// Reference: /root/reference/code/modelv2/layers.py:19-27
+//     beta  = beta_param**2 - 2^-18                      (:20)   two roundings
+//     gamma = gamma_conv.weight**2 - 2^-18               (:21)   two roundings
+//     denom = sqrt(beta + conv2d(x**2, gamma, groups=C)) (:23)   x2=rn(x*x); p=rn(gamma*x2); s=rn(beta+p); d=sqrt_rn(s)
+//     y     = x*denom (inverse) | x/denom                (:24-27) rn(x*d) | div_rn(x,d)
+// The eager path is 5 launches / ~11 tensor passes; this is one pass at 8 B/element (fwd) and 12 B/element (bwd, the
+// denominator is recomputed instead of saved).  Both are HBM-bound streaming kernels: 128-bit L1-bypassing accesses,
+// 4 vectors in flight per thread, grid sized to a multiple of the SM count.
+//
+// Forward uses only __f*_rn intrinsics so ptxas cannot contract mul+add into an FMA: a fused beta+gamma*x2 differs in
+// the last bit and would flip round() on latents that sit on a half-integer.
+#include "common.cuh"
+
+namespace sic {
+namespace {
+
+constexpr float kOffset = 3.814697265625e-06f;  // 2^-18, layers.py:8
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+constexpr int kChunk4 = 2048;  // float4 per backward unit (8192 elements)
+
+// n / d for n < 2^31 with one mul-hi (Granlund-Montgomery, as in ATen's IntDivider)
+struct FastDiv {
+    unsigned d, magic, shift;
+    FastDiv() : d(1), magic(0), shift(0) {}
+    explicit FastDiv(unsigned div) : d(div) {
+        for (shift = 0; shift < 32; ++shift)
+            if ((1u << shift) >= d) break;
+        uint64_t one = 1;
+        magic = (unsigned)(((one << 32) * ((one << shift) - d)) / d + 1);
+    }
+    __device__ __forceinline__ unsigned div(unsigned n) const { return (__umulhi(n, magic) + n) >> shift; }
+};
+
+__device__ __forceinline__ void eff_params(const float *__restrict__ beta_param, const float *__restrict__ gamma_weight, int c,
+                                           float &beta, float &gamma) {
+    float b = __ldg(beta_param + c), w = __ldg(gamma_weight + c);
+    beta = __fadd_rn(__fmul_rn(b, b), -kOffset);   // layers.py:20
+    gamma = __fadd_rn(__fmul_rn(w, w), -kOffset);  // layers.py:21
+}
+
+template <bool INVERSE>
+__device__ __forceinline__ float gdn1(float x, float beta, float gamma) {
+    float x2 = __fmul_rn(x, x);
+    float p = __fmul_rn(gamma, x2);
+    float s = __fadd_rn(beta, p);
+    float d = __fsqrt_rn(s);
+    return INVERSE ? __fmul_rn(x, d) : __fdiv_rn(x, d);
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(kThreads) gdn_fwd_vec_kernel(const float4 *__restrict__ x, const float *__restrict__ beta_param,
+                                                               const float *__restrict__ gamma_weight, unsigned n4, FastDiv hw4,
+                                                               FastDiv chan, float4 *__restrict__ y) {
+    const unsigned stride = gridDim.x * kThreads * kUnroll;
+    for (unsigned v0 = blockIdx.x * (kThreads * kUnroll) + threadIdx.x; v0 < n4; v0 += stride) {
+        float4 a[kUnroll];
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+            unsigned v = v0 + k * kThreads;
+            if (v < n4) a[k] = ldg_stream(x + v);
+        }
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+            unsigned v = v0 + k * kThreads;
+            if (v < n4) {
+                unsigned plane = hw4.div(v);
+                unsigned c = plane - chan.div(plane) * chan.d;
+                float beta, gamma;
+                eff_params(beta_param, gamma_weight, (int)c, beta, gamma);
+                float4 o;
+                o.x = gdn1<INVERSE>(a[k].x, beta, gamma);
+                o.y = gdn1<INVERSE>(a[k].y, beta, gamma);
+                o.z = gdn1<INVERSE>(a[k].z, beta, gamma);
+                o.w = gdn1<INVERSE>(a[k].w, beta, gamma);
+                stg_stream(y + v, o);
+            }
+        }
+    }
+}
+
+template <bool INVERSE>
+__global__ void __launch_bounds__(kThreads) gdn_fwd_scalar_kernel(const float *__restrict__ x, const float *__restrict__ beta_param,
+                                                                  const float *__restrict__ gamma_weight, long n, int HW, int C,
+                                                                  int channels_last, float *__restrict__ y) {
+    for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long)gridDim.x * kThreads) {
+        int c = channels_last ? (int)(i % C) : (int)((i / HW) % C);
+        float beta, gamma;
+        eff_params(beta_param, gamma_weight, c, beta, gamma);
+        y[i] = gdn1<INVERSE>(x[i], beta, gamma);
+    }
+}
+
+// channels-last (NHWC) vector path: 4 consecutive elements are 4 consecutive channels (C % 4 == 0)
+template <bool INVERSE>
+__global__ void __launch_bounds__(kThreads) gdn_fwd_nhwc_kernel(const float4 *__restrict__ x, const float *__restrict__ beta_param,
+                                                                const float *__restrict__ gamma_weight, unsigned n4, FastDiv c4,
+                                                                float4 *__restrict__ y) {
+    const unsigned stride = gridDim.x * kThreads * kUnroll;
+    for (unsigned v0 = blockIdx.x * (kThreads * kUnroll) + threadIdx.x; v0 < n4; v0 += stride) {
+        float4 a[kUnroll];
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+            unsigned v = v0 + k * kThreads;
+            if (v < n4) a[k] = ldg_stream(x + v);
+        }
+#pragma unroll
+        for (int k = 0; k < kUnroll; ++k) {
+            unsigned v = v0 + k * kThreads;
+            if (v < n4) {
+                int c = (int)(v - c4.div(v) * c4.d) * 4;
+                float b0, g0, b1, g1, b2, g2, b3, g3;
+                eff_params(beta_param, gamma_weight, c, b0, g0);
+                eff_params(beta_param, gamma_weight, c + 1, b1, g1);
+                eff_params(beta_param, gamma_weight, c + 2, b2, g2);
+                eff_params(beta_param, gamma_weight, c + 3, b3, g3);
+                float4 o;
+                o.x = gdn1<INVERSE>(a[k].x, b0, g0);
+                o.y = gdn1<INVERSE>(a[k].y, b1, g1);
+                o.z = gdn1<INVERSE>(a[k].z, b2, g2);
+                o.w = gdn1<INVERSE>(a[k].w, b3, g3);
+                stg_stream(y + v, o);
+            }
+        }
+    }
+}
+
+// ---- backward ------------------------------------------------------------------------------------------------------
+// GDN : y = x/d    dx = g*beta/d^3            h = -1/2 g x / d^3
+// IGDN: y = x*d    dx = g*(s + gamma x^2)/d   h = +1/2 g x / d          dbeta_c = sum h ; dgamma_c = sum h x^2
+template <bool INVERSE>
+__device__ __forceinline__ void gdn_bwd1(float x, float g, float beta, float gamma, float &dx, float &hb, float &hg) {
+    float x2 = x * x;
+    float gx2 = gamma * x2;
+    float s = beta + gx2;
+    float r = rsqrtf(s);
+    if (INVERSE) {
+        dx = g * (s + gx2) * r;
+        hb = 0.5f * g * x * r;
+    } else {
+        float r3 = r * r * r;
+        dx = g * beta * r3;
+        hb = -0.5f * g * x * r3;
+    }
+    hg = hb * x2;
+}
+
+__device__ __forceinline__ void block_sum2(float &a, float &b) {
+    __shared__ float sa[kThreads / 32], sb[kThreads / 32];
+    a = warp_sum(a);
+    b = warp_sum(b);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sa[warp] = a; sb[warp] = b; }
+    __syncthreads();
+    if (warp == 0) {
+        a = lane < kThreads / 32 ? sa[lane] : 0.f;
+        b = lane < kThreads / 32 ? sb[lane] : 0.f;
+        a = warp_sum(a);
+        b = warp_sum(b);
+    }
+}
+
+// one CTA = one (plane, chunk) unit; partials laid out [C][B*chunks] so the finalize kernel reads them contiguously
+template <bool INVERSE, bool VEC>
+__global__ void __launch_bounds__(kThreads) gdn_bwd_kernel(const float *__restrict__ x, const float *__restrict__ g,
+                                                           const float *__restrict__ beta_param, const float *__restrict__ gamma_weight,
+                                                           int C, int HW, int chunks, float *__restrict__ dx, float *__restrict__ part) {
+    const int plane = blockIdx.x / chunks;
+    const int chunk = blockIdx.x - plane * chunks;
+    const int c = plane % C, b = plane / C;
+    float beta, gamma;
+    eff_params(beta_param, gamma_weight, c, beta, gamma);
+    float acc_b = 0.f, acc_g = 0.f;
+    const long base = (long)plane * HW;
+    if (VEC) {
+        const int hw4 = HW >> 2;
+        const int v_begin = chunk * kChunk4, v_end = min(v_begin + kChunk4, hw4);
+        const float4 *x4 = reinterpret_cast<const float4 *>(x + base), *g4 = reinterpret_cast<const float4 *>(g + base);
+        float4 *dx4 = reinterpret_cast<float4 *>(dx + base);
+        constexpr int U = 2;
+        for (int v0 = v_begin + threadIdx.x; v0 < v_end; v0 += kThreads * U) {
+            float4 xa[U], ga[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                int v = v0 + k * kThreads;
+                if (v < v_end) { xa[k] = ldg_stream(x4 + v); ga[k] = ldg_stream(g4 + v); }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                int v = v0 + k * kThreads;
+                if (v < v_end) {
+                    float4 o;
+                    float hb, hg;
+                    gdn_bwd1<INVERSE>(xa[k].x, ga[k].x, beta, gamma, o.x, hb, hg); acc_b += hb; acc_g += hg;
+                    gdn_bwd1<INVERSE>(xa[k].y, ga[k].y, beta, gamma, o.y, hb, hg); acc_b += hb; acc_g += hg;
+                    gdn_bwd1<INVERSE>(xa[k].z, ga[k].z, beta, gamma, o.z, hb, hg); acc_b += hb; acc_g += hg;
+                    gdn_bwd1<INVERSE>(xa[k].w, ga[k].w, beta, gamma, o.w, hb, hg); acc_b += hb; acc_g += hg;
+                    stg_stream(dx4 + v, o);
+                }
+            }
+        }
+    } else {
+        const int e_begin = chunk * kChunk4 * 4, e_end = min(e_begin + kChunk4 * 4, HW);
+        for (int e = e_begin + threadIdx.x; e < e_end; e += kThreads) {
+            float o, hb, hg;
+            gdn_bwd1<INVERSE>(x[base + e], g[base + e], beta, gamma, o, hb, hg);
+            dx[base + e] = o;
+            acc_b += hb;
+            acc_g += hg;
+        }
+    }
+    block_sum2(acc_b, acc_g);
+    if (threadIdx.x == 0) {
+        const long P = (long)gridDim.x / C;  // = B * chunks partials per channel
+        long slot = (long)c * P + (long)b * chunks + chunk;
+        part[slot] = acc_b;
+        part[(long)C * P + slot] = acc_g;
+    }
+}
+
+// one CTA per channel: fixed-order float64 fold + chain rule through the squared re-parameterisation (layers.py:20-21)
+__global__ void __launch_bounds__(128) gdn_bwd_finalize_kernel(const float *__restrict__ part, const float *__restrict__ beta_param,
+                                                               const float *__restrict__ gamma_weight, int C, long P,
+                                                               float *__restrict__ dbeta_param, float *__restrict__ dgamma_weight) {
+    const int c = blockIdx.x;
+    double sb = 0.0, sg = 0.0;
+    for (long i = threadIdx.x; i < P; i += 128) {
+        sb += (double)part[(long)c * P + i];
+        sg += (double)part[(long)C * P + (long)c * P + i];
+    }
+    __shared__ double shb[4], shg[4];
+    sb = warp_sum(sb);
+    sg = warp_sum(sg);
+    if ((threadIdx.x & 31) == 0) { shb[threadIdx.x >> 5] = sb; shg[threadIdx.x >> 5] = sg; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sb = (shb[0] + shb[1]) + (shb[2] + shb[3]);
+        sg = (shg[0] + shg[1]) + (shg[2] + shg[3]);
+        if (dbeta_param) dbeta_param[c] = (float)(sb * 2.0 * (double)beta_param[c]);
+        if (dgamma_weight) dgamma_weight[c] = (float)(sg * 2.0 * (double)gamma_weight[c]);
+    }
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int bwd_chunks(int HW) {
+    int per = kChunk4 * 4;
+    return (HW + per - 1) / per;
+}
+
+}  // namespace
+}  // namespace sic
+
+using namespace sic;
+
+extern "C" int sic_gdn_fwd(const float *x, const float *beta_param, const float *gamma_weight, int B, int C, int HW, int inverse,
+                           int channels_last, float *y, void *stream) {
+    SIC_CHECK_ARG(B > 0 && C > 0 && HW > 0, "sic_gdn_fwd: empty shape B=%d C=%d HW=%d", B, C, HW);
+    SIC_CHECK_ARG(x && y && beta_param && gamma_weight, "sic_gdn_fwd: null pointer");
+    const long n = (long)B * C * HW;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = sm_count();
+    const bool al = aligned16(x) && aligned16(y) && n / 4 < (1L << 31);
+    if (!channels_last && HW % 4 == 0 && al) {
+        unsigned n4 = (unsigned)(n / 4);
+        long want = ((long)n4 + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+        unsigned grid = (unsigned)(want < (long)sms * 8 ? want : (long)sms * 8);
+        FastDiv hw4((unsigned)(HW / 4)), chan((unsigned)C);
+        if (inverse) gdn_fwd_vec_kernel<true><<<grid, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, hw4, chan, (float4 *)y);
+        else gdn_fwd_vec_kernel<false><<<grid, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, hw4, chan, (float4 *)y);
+    } else if (channels_last && C % 4 == 0 && al) {
+        unsigned n4 = (unsigned)(n / 4);
+        long want = ((long)n4 + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+        unsigned grid = (unsigned)(want < (long)sms * 8 ? want : (long)sms * 8);
+        FastDiv c4((unsigned)(C / 4));
+        if (inverse) gdn_fwd_nhwc_kernel<true><<<grid, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, c4, (float4 *)y);
+        else gdn_fwd_nhwc_kernel<false><<<grid, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, c4, (float4 *)y);
+    } else {
+        long want = (n + kThreads - 1) / kThreads;
+        unsigned grid = (unsigned)(want < (long)sms * 16 ? want : (long)sms * 16);
+        if (inverse) gdn_fwd_scalar_kernel<true><<<grid, kThreads, 0, st>>>(x, beta_param, gamma_weight, n, HW, C, channels_last, y);
+        else gdn_fwd_scalar_kernel<false><<<grid, kThreads, 0, st>>>(x, beta_param, gamma_weight, n, HW, C, channels_last, y);
+    }
+    SIC_CHECK_LAUNCH("sic_gdn_fwd");
+    return 0;
+}
+
+extern "C" size_t sic_gdn_bwd_workspace_bytes(int B, int C, int HW) {
+    if (B <= 0 || C <= 0 || HW <= 0) return 0;
+    return (size_t)2 * C * B * bwd_chunks(HW) * sizeof(float);
+}
+
+extern "C" int sic_gdn_bwd(const float *x, const float *g, const float *beta_param, const float *gamma_weight, int B, int C,
+                           int HW, int inverse, int channels_last, float *dx, float *dbeta_param, float *dgamma_weight,
+                           void *workspace, size_t workspace_bytes, void *stream) {
+    SIC_CHECK_ARG(B > 0 && C > 0 && HW > 0, "sic_gdn_bwd: empty shape B=%d C=%d HW=%d", B, C, HW);
+    SIC_CHECK_ARG(x && g && dx && beta_param && gamma_weight && workspace, "sic_gdn_bwd: null pointer");
+    if (channels_last) {
+        set_error("sic_gdn_bwd: channels_last layout not implemented");
+        return SIC_E_UNSUPPORTED;
+    }
+    if (workspace_bytes < sic_gdn_bwd_workspace_bytes(B, C, HW)) {
+        set_error("sic_gdn_bwd: workspace %zu < %zu bytes", workspace_bytes, sic_gdn_bwd_workspace_bytes(B, C, HW));
+        return SIC_E_WORKSPACE;
+    }
+    const int chunks = bwd_chunks(HW);
+    const long units = (long)B * C * chunks;
+    SIC_CHECK_ARG(units < (1L << 31), "sic_gdn_bwd: too many units");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *part = static_cast<float *>(workspace);
+    const bool vec = HW % 4 == 0 && aligned16(x) && aligned16(g) && aligned16(dx);
+    if (inverse) {
+        if (vec) gdn_bwd_kernel<true, true><<<(unsigned)units, kThreads, 0, st>>>(x, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
+        else gdn_bwd_kernel<true, false><<<(unsigned)units, kThreads, 0, st>>>(x, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
+    } else {
+        if (vec) gdn_bwd_kernel<false, true><<<(unsigned)units, kThreads, 0, st>>>(x, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
+        else gdn_bwd_kernel<false, false><<<(unsigned)units, kThreads, 0, st>>>(x, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
+    }
+    SIC_CHECK_LAUNCH("sic_gdn_bwd");
+    gdn_bwd_finalize_kernel<<<C, 128, 0, st>>>(part, beta_param, gamma_weight, C, (long)B * chunks, dbeta_param, dgamma_weight);
+    SIC_CHECK_LAUNCH("sic_gdn_bwd finalize");
+    return 0;
+}

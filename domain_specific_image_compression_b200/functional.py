@@ -1,0 +1,269 @@
+"""torch.autograd front ends of the C-ABI kernels (include/sic.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every number is produced by libsic.so.  Inputs must
+be CUDA float32 tensors — there is no CPU or eager fallback (the CPU oracle lives in /oracle and is test-only).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (LIK_GAUSSIAN, LIK_STUDENTT_CDFDIFF, LIK_STUDENTT_DENSITY, PARAM_BROADCAST, PARAM_CHANNEL,
+                   PARAM_SPATIAL, QUANT_NOISE_PHILOX, QUANT_NOISE_TENSOR, QUANT_NONE, QUANT_ROUND)
+
+_QUANT = {"none": QUANT_NONE, "round": QUANT_ROUND, "noise": QUANT_NOISE_PHILOX}
+_LIK = {"density": LIK_STUDENTT_DENSITY, "gaussian": LIK_GAUSSIAN, "cdf_diff": LIK_STUDENTT_CDFDIFF}
+
+# ----------------------------------------------------------------------------------------------------------------------
+# plumbing
+_workspaces = {}
+_philox = {}
+launch_count = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.SicError(f"{name}: expected a CUDA tensor — this package has no CPU path (the CPU oracle is oracle/, test only)")
+    if t.dtype != torch.float32:
+        raise _lib.SicError(f"{name}: expected float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Zero-initialised scratch, one per (device, stream); kernels leave it zeroed (ticket counters self-reset)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def philox_state(device: torch.device) -> torch.Tensor:
+    """Device-resident {seed, offset} for the in-kernel noise; re-seeded whenever torch.manual_seed changes."""
+    seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+    st = _philox.get(device.index)
+    if st is None or st[0] != seed:
+        t = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        _philox[device.index] = (seed, t)
+        return t
+    return st[1]
+
+
+def _launch(rc: int, what: str) -> None:
+    global launch_count
+    _lib.check(rc, what)
+    launch_count += 1
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K1
+class _Bottleneck(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, sigma, nu, mu, noise, quant_mode: int, lik_mode: int, layout: int, want_nll: bool):
+        lib = _lib.load()
+        y = _require_cuda_f32(y, "y")
+        sigma = _require_cuda_f32(sigma, "sigma")
+        nu = _require_cuda_f32(nu, "nu") if nu is not None else None
+        mu = _require_cuda_f32(mu, "mu") if mu is not None else None
+        B, C = y.shape[0], y.shape[1]
+        HW = y.numel() // (B * C)
+        n_par = {PARAM_BROADCAST: B * C, PARAM_SPATIAL: y.numel(), PARAM_CHANNEL: C}[layout]
+        for t, nm in ((sigma, "sigma"), (nu, "nu"), (mu, "mu")):
+            if t is not None and t.numel() != n_par:
+                raise _lib.SicError(f"{nm}: {t.numel()} values, layout needs {n_par}")
+        philox = None
+        if quant_mode == QUANT_NOISE_TENSOR:
+            noise = _require_cuda_f32(noise, "noise")
+            if noise.shape != y.shape:
+                raise _lib.SicError("noise must have the shape of y")
+        elif quant_mode == QUANT_NOISE_PHILOX:
+            philox = philox_state(y.device)
+        y_tilde = torch.empty_like(y) if quant_mode != QUANT_NONE else None
+        nll = torch.empty_like(y) if want_nll else None
+        bits = torch.empty(B, dtype=torch.float32, device=y.device)
+        nws = lib.sic_bottleneck_workspace_bytes(B, C, HW)
+        ws = _workspace(y.device, nws)
+        with torch.cuda.device(y.device):
+            _launch(lib.sic_bottleneck_fwd(_ptr(y), _ptr(noise), _ptr(philox), _ptr(mu), _ptr(sigma), _ptr(nu), B, C, HW,
+                                           quant_mode, lik_mode, layout, _ptr(y_tilde), _ptr(nll), _ptr(bits), _ptr(ws),
+                                           ws.numel(), _stream()), "sic_bottleneck_fwd")
+        if quant_mode == QUANT_NONE:
+            y_tilde = y
+        ctx.save_for_backward(y_tilde, sigma, nu, mu)
+        ctx.cfg = (B, C, HW, quant_mode, lik_mode, layout)
+        ctx.shapes = (sigma.shape, None if nu is None else nu.shape, None if mu is None else mu.shape)
+        ctx.set_materialize_grads(False)
+        return (y_tilde if quant_mode != QUANT_NONE else None), nll, bits
+
+    @staticmethod
+    def backward(ctx, g_yt, g_nll, g_bits):
+        lib = _lib.load()
+        y_tilde, sigma, nu, mu = ctx.saved_tensors
+        B, C, HW, quant_mode, lik_mode, layout = ctx.cfg
+        need_y, need_s, need_n, need_m = ctx.needs_input_grad[:4]
+        g_yt = None if g_yt is None else _require_cuda_f32(g_yt, "g_ytilde")
+        g_nll = None if g_nll is None else _require_cuda_f32(g_nll, "g_nll")
+        g_bits = None if g_bits is None else _require_cuda_f32(g_bits, "g_bits")
+        dy = torch.empty_like(y_tilde) if need_y else None
+        dsigma = torch.empty_like(sigma) if need_s else None
+        dnu = torch.empty_like(nu) if (need_n and nu is not None) else None
+        dmu = torch.empty_like(mu) if (need_m and mu is not None) else None
+        ws = _workspace(y_tilde.device, lib.sic_bottleneck_workspace_bytes(B, C, HW))
+        with torch.cuda.device(y_tilde.device):
+            _launch(lib.sic_bottleneck_bwd(_ptr(y_tilde), _ptr(mu), _ptr(sigma), _ptr(nu), _ptr(g_nll), _ptr(g_bits), _ptr(g_yt),
+                                           B, C, HW, quant_mode, lik_mode, layout, _ptr(dy), _ptr(dmu), _ptr(dsigma), _ptr(dnu),
+                                           _ptr(ws), ws.numel(), _stream()), "sic_bottleneck_bwd")
+        return dy, dsigma, dnu, dmu, None, None, None, None, None
+
+
+def bottleneck(y: torch.Tensor, sigma: torch.Tensor, nu: Optional[torch.Tensor] = None, mu: Optional[torch.Tensor] = None,
+               *, quant: str = "noise", lik: str = "density", noise: Optional[torch.Tensor] = None,
+               want_nll: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
+    """Fused quantise + likelihood + rate (K1).  Returns (y_tilde, nll, bits[B]).
+
+    sigma / nu / mu: [B,C,1,1] (or [B,C]) -> broadcast layout; same shape as y -> spatial layout; for lik='gaussian'
+    `sigma` is the per-channel log_sigma parameter [C].  quant: 'noise' | 'round' | 'none'; pass `noise=` to supply the
+    uniform draw (parity mode) instead of the in-kernel Philox generator."""
+    if quant not in _QUANT:
+        raise ValueError(f"Unknown quant mode: {quant}")            # model.py:35
+    q = _QUANT[quant]
+    if quant == "noise" and noise is not None:
+        q = QUANT_NOISE_TENSOR
+    lik_mode = _LIK[lik]
+    if lik == "gaussian":
+        layout = PARAM_CHANNEL
+    elif sigma.numel() == y.numel():
+        layout = PARAM_SPATIAL
+    elif sigma.numel() == y.shape[0] * y.shape[1]:
+        layout = PARAM_BROADCAST
+    else:
+        raise _lib.SicError(f"sigma with {tuple(sigma.shape)} is neither per-(b,c) nor per-element for y {tuple(y.shape)}")
+    y_tilde, nll, bits = _Bottleneck.apply(y, sigma, nu, mu, noise, q, lik_mode, layout, want_nll)
+    return (y if y_tilde is None else y_tilde), nll, bits
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K2
+class _GDN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, beta_param, gamma_weight, inverse: bool):
+        lib = _lib.load()
+        x = _require_cuda_f32(x, "x")
+        beta_param = _require_cuda_f32(beta_param, "beta")
+        gamma_weight = _require_cuda_f32(gamma_weight, "gamma_conv.weight")
+        B, C = x.shape[0], x.shape[1]
+        if beta_param.numel() != C or gamma_weight.numel() != C:
+            raise _lib.SicError(f"GDN parameters have {beta_param.numel()}/{gamma_weight.numel()} entries for {C} channels")
+        HW = x.numel() // (B * C)
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _launch(lib.sic_gdn_fwd(_ptr(x), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, int(inverse), 0, _ptr(y), _stream()),
+                    "sic_gdn_fwd")
+        ctx.save_for_backward(x, beta_param, gamma_weight)
+        ctx.cfg = (B, C, HW, int(inverse))
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, beta_param, gamma_weight = ctx.saved_tensors
+        B, C, HW, inverse = ctx.cfg
+        g = _require_cuda_f32(g, "grad_output")
+        dx = torch.empty_like(x)
+        dbeta = torch.empty_like(beta_param)
+        dgamma = torch.empty_like(gamma_weight)
+        nws = lib.sic_gdn_bwd_workspace_bytes(B, C, HW)
+        ws = _workspace(x.device, nws)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.sic_gdn_bwd(_ptr(x), _ptr(g), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, inverse, 0, _ptr(dx),
+                                       _ptr(dbeta), _ptr(dgamma), _ptr(ws), ws.numel(), _stream()), "sic_gdn_bwd")
+        global launch_count
+        launch_count += 2
+        return dx, dbeta, dgamma, None
+
+
+def gdn(x: torch.Tensor, beta_param: torch.Tensor, gamma_weight: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+    """Diagonal GDN/IGDN (K2), bit-exact with layers.py:19-27 on the same device arithmetic."""
+    return _GDN.apply(x, beta_param, gamma_weight, inverse)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K4 / K3 / E1
+def quantize_indices(q: torch.Tensor, do_round: bool = False, tail: int = 10, want_symbols: bool = True):
+    """Per-patch support and symbols (K4): returns (sym int32 like q, mins int32 [B], maxs int32 [B]) on the device."""
+    lib = _lib.load()
+    q = _require_cuda_f32(q, "q")
+    B = q.shape[0]
+    n_per = q.numel() // B
+    sym = torch.empty(q.shape, dtype=torch.int32, device=q.device) if want_symbols else None
+    mins = torch.empty(B, dtype=torch.int32, device=q.device)
+    maxs = torch.empty(B, dtype=torch.int32, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(lib.sic_quantize_indices(_ptr(q), B, n_per, int(do_round), int(tail), _ptr(sym), _ptr(mins), _ptr(maxs),
+                                            _stream()), "sic_quantize_indices")
+    global launch_count
+    launch_count += 4 if want_symbols else 3
+    return sym, mins, maxs
+
+
+def build_cdf_tables(kind: str, sigma: torch.Tensor, nu: Optional[torch.Tensor], n_patches: int, mins: torch.Tensor,
+                     maxs: torch.Tensor, stride: int, channels: Optional[int] = None) -> torch.Tensor:
+    """uint16 CDF tables [n_rows, stride] (K3).  kind 'gaussian': sigma = log_sigma[C], one row per (patch, channel);
+    kind 'studentt': sigma/nu raw, n_rows = sigma.numel(), rows split evenly over the patches."""
+    lib = _lib.load()
+    sigma = _require_cuda_f32(sigma, "sigma")
+    if kind == "gaussian":
+        C = sigma.numel()
+        n_rows, rows_per_patch, k = n_patches * C, C, 0
+    elif kind == "studentt":
+        nu = _require_cuda_f32(nu, "nu")
+        n_rows = sigma.numel()
+        if n_rows % n_patches or nu.numel() != n_rows:
+            raise _lib.SicError("sigma/nu row count must be a multiple of the patch count")
+        rows_per_patch, C, k = n_rows // n_patches, channels or (n_rows // n_patches), 1
+    else:
+        raise ValueError("kind must be 'gaussian' or 'studentt'")
+    if mins.dtype != torch.int32 or maxs.dtype != torch.int32 or not mins.is_cuda:
+        raise _lib.SicError("mins/maxs must be CUDA int32 tensors")
+    out = torch.empty((n_rows, stride), dtype=torch.uint16, device=sigma.device)
+    with torch.cuda.device(sigma.device):
+        _launch(lib.sic_build_cdf_tables(k, _ptr(sigma), _ptr(nu), n_rows, rows_per_patch, C, _ptr(mins.contiguous()),
+                                         _ptr(maxs.contiguous()), int(stride), _ptr(out), _stream()), "sic_build_cdf_tables")
+    return out
+
+
+def rans_encode(sym: np.ndarray, tables: np.ndarray, L: int, sym_per_row: int) -> bytes:
+    """Host rANS encoder (E1, SIC-RANS-1).  sym int32 [n], tables uint16 [rows, stride]."""
+    lib = _lib.load()
+    sym = np.ascontiguousarray(sym, np.int32).ravel()
+    tables = np.ascontiguousarray(tables, np.uint16)
+    cap = 128 + 2 * sym.size + 16
+    out = np.empty(cap, np.uint8)
+    n = lib.sic_rans_encode_host(sym.ctypes.data, sym.size, tables.ctypes.data, tables.shape[-1], int(L), int(sym_per_row),
+                                 out.ctypes.data, cap)
+    if n < 0:
+        _lib.check(int(n), "sic_rans_encode_host")
+    return out[:n].tobytes()
+
+
+def rans_decode(data: bytes, n: int, tables: np.ndarray, L: int, sym_per_row: int) -> np.ndarray:
+    lib = _lib.load()
+    tables = np.ascontiguousarray(tables, np.uint16)
+    buf = np.frombuffer(data, np.uint8)
+    sym = np.empty(int(n), np.int32)
+    _lib.check(lib.sic_rans_decode_host(buf.ctypes.data, buf.size, int(n), tables.ctypes.data, tables.shape[-1], int(L),
+                                        int(sym_per_row), sym.ctypes.data), "sic_rans_decode_host")
+    return sym

@@ -1,0 +1,126 @@
+"""Transforms of the autoencoder, state_dict-compatible with /root/reference/code/modelv2/layers.py.
+
+GDN/IGDN run the fused CUDA kernel K2; the convolutions stay on cuDNN exactly as in the reference (project goal).
+Module and parameter names match the reference so that its checkpoints load unchanged: `g_a.g_a.<i>`, `g_s.g_s.<i>`,
+`h_a.h_a.<i>`, `h_s.h_s.<i>`, `h_s.mlp_sigma/mlp_nu.<i>` (or `h_s.to_sigma/to_nu`), and per GDN site
+`beta [C]`, `gamma [C,C]` (stored but unused by the reference's forward, layers.py:13 vs :21) and `gamma_conv.weight [C,1,1,1]`.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import functional as F_sic
+
+
+class GDN(nn.Module):
+    """y = x / sqrt(beta + gamma * x^2) per channel (inverse: multiply), layers.py:6-27."""
+
+    def __init__(self, channels, inverse=False, beta_min=1e-6, gamma_init=0.1, reparam_offset=2**-18):
+        super().__init__()
+        if reparam_offset != 2**-18:
+            raise ValueError("the CUDA kernel fixes reparam_offset at 2**-18 (the reference never passes another value)")
+        self.inverse = inverse
+        self.reparam_offset = reparam_offset
+        self.beta = nn.Parameter(torch.sqrt(torch.ones(channels) + reparam_offset))                       # layers.py:12
+        self.gamma = nn.Parameter(torch.sqrt(torch.eye(channels) * gamma_init + reparam_offset))           # layers.py:13 (dead)
+        self.gamma_conv = nn.Conv2d(channels, channels, kernel_size=1, groups=channels, bias=False)        # layers.py:15
+        with torch.no_grad():
+            self.gamma_conv.weight.copy_(self.gamma.diag().view(channels, 1, 1, 1))                        # layers.py:16-17
+
+    def forward(self, x):
+        return F_sic.gdn(x, self.beta, self.gamma_conv.weight, self.inverse)
+
+
+def _conv(cin, cout, k, stride=1):
+    return nn.Conv2d(cin, cout, k, stride=stride, padding=(k - 1) // 2)          # layers.py:29-31
+
+
+def _deconv(cin, cout):
+    return nn.ConvTranspose2d(cin, cout, 5, 2, 2, output_padding=1)              # layers.py:83 etc.
+
+
+def _stack(spec):
+    """spec: list of ('c', cin, cout, k, stride) | ('d', cin, cout) | ('g', C) | ('ig', C) | ('r',) -> nn.Sequential."""
+    mods = []
+    for item in spec:
+        kind = item[0]
+        if kind == "c":
+            mods.append(_conv(*item[1:]))
+        elif kind == "d":
+            mods.append(_deconv(*item[1:]))
+        elif kind == "g":
+            mods.append(GDN(item[1]))
+        elif kind == "ig":
+            mods.append(GDN(item[1], inverse=True))
+        elif kind == "r":
+            mods.append(nn.ReLU(inplace=True))
+    return nn.Sequential(*mods)
+
+
+class AnalysisTransform(nn.Module):
+    """8 convs + 7 GDN, four stride-2 stages: x [B,3,H,W] -> y [B,M,H/16,W/16]   (layers.py:46-76)."""
+
+    def __init__(self, N=128, M=192):
+        super().__init__()
+        spec = [("c", 3, N, 3, 1), ("g", N)]
+        for _ in range(3):
+            spec += [("c", N, N, 5, 2), ("g", N), ("c", N, N, 3, 1), ("g", N)]
+        spec += [("c", N, M, 5, 2)]
+        self.g_a = _stack(spec)
+
+    def forward(self, x):
+        return self.g_a(x)
+
+
+class SynthesisTransform(nn.Module):
+    """4 transposed convs + 3 convs + 6 IGDN: y_hat [B,M,h,w] -> x_hat [B,3,16h,16w]   (layers.py:78-101)."""
+
+    def __init__(self, N=128, M=192):
+        super().__init__()
+        spec = [("d", M, N), ("ig", N), ("c", N, N, 3, 1), ("ig", N)]
+        for _ in range(2):
+            spec += [("d", N, N), ("ig", N), ("c", N, N, 3, 1), ("ig", N)]
+        spec += [("d", N, 3)]
+        self.g_s = _stack(spec)
+
+    def forward(self, y_hat):
+        return self.g_s(y_hat)
+
+
+class HyperAnalysis(nn.Module):
+    """y [B,M,h,w] -> z [B,N,h/4,w/4]   (layers.py:104-116)."""
+
+    def __init__(self, M=192, N=128):
+        super().__init__()
+        self.h_a = _stack([("c", M, N, 3, 1), ("r",), ("c", N, N, 3, 1), ("r",), ("c", N, N, 5, 2), ("r",), ("c", N, N, 5, 2)])
+
+    def forward(self, y):
+        return self.h_a(y)
+
+
+class HyperSynthesis(nn.Module):
+    """z_hat -> (log_sigma, log_nu) of the Student-t over y   (layers.py:118-152).
+
+    spatial_params=False: global average pool + two 1x1-conv MLPs, result expand()-ed over (h,w) as stride-0 views;
+    spatial_params=True: two 3x3 conv heads producing dense maps."""
+
+    def __init__(self, N=128, M=128, spatial_params=False):
+        super().__init__()
+        self.spatial_params = spatial_params
+        self.h_s = _stack([("d", N, N), ("r",), ("d", N, N), ("r",)])
+        if spatial_params:
+            self.to_sigma = _conv(N, M, 3, 1)
+            self.to_nu = _conv(N, M, 3, 1)
+        else:
+            self.pool = nn.AdaptiveAvgPool2d(1)
+            self.mlp_sigma = nn.Sequential(nn.Conv2d(N, N, 1), nn.ReLU(), nn.Conv2d(N, M, 1))
+            self.mlp_nu = nn.Sequential(nn.Conv2d(N, N, 1), nn.ReLU(), nn.Conv2d(N, M, 1))
+
+    def forward(self, z):
+        t = self.h_s(z)
+        if self.spatial_params:
+            return self.to_sigma(t), self.to_nu(t)
+        p = self.pool(t)
+        h, w = t.size(2), t.size(3)
+        return self.mlp_sigma(p).expand(-1, -1, h, w), self.mlp_nu(p).expand(-1, -1, h, w)

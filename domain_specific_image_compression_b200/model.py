@@ -1,0 +1,182 @@
+"""CompressionModel / rate_distortion_loss with the API of /root/reference/code/modelv2/model.py, plus compress() /
+decompress() methods that carry the semantics of custom_compress / custom_decompress
+(/root/reference/code/modelv2/eval_selfcontained_entropy.py:26-123).
+
+Drop-in contract: constructor signature, `forward(x, quant_mode)` returning exactly the nine keys
+x_hat, nll_y, nll_z, y, y_tilde, z, z_tilde, sigma, nu; static `quantize`; `rate_distortion_loss(out, x, lambda_rd, dist)`
+returning (loss, R.detach(), D.detach()); 90 state_dict keys identical to the reference's.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as F_sic
+from .distributions import FactorizedGaussian, StudentT
+from .layers import AnalysisTransform, HyperAnalysis, HyperSynthesis, SynthesisTransform
+from .losses import multi_scale_ssim
+
+
+class CompressionModel(nn.Module):
+    def __init__(self, N=128, M=192, spatial_params=False, min_nu=1.1, max_nu=100.0, likelihood: str = "density"):
+        super().__init__()
+        self.g_a = AnalysisTransform(N, M)
+        self.g_s = SynthesisTransform(N, M)
+        self.h_a = HyperAnalysis(M, N)
+        self.h_s = HyperSynthesis(N, M, spatial_params=spatial_params)
+        self.studentT = StudentT(mode=likelihood)
+        self.z_prior = FactorizedGaussian(N)
+        self.min_nu = min_nu
+        self.max_nu = max_nu
+        self.spatial_params = spatial_params
+        self.likelihood = likelihood          # 'density' (what the reference trains with) | 'cdf_diff' (north_star variant)
+
+    @staticmethod
+    def quantize(x, mode):
+        """model.py:27-35.  Standalone helper kept for API parity; forward() fuses quantisation into kernel K1."""
+        if mode == "noise":
+            return x + torch.empty_like(x).uniform_(-0.5, 0.5)
+        if mode == "round":
+            return torch.round(x)
+        raise ValueError(f"Unknown quant mode: {mode}")
+
+    def _student_params(self, z_tilde, like):
+        """model.py:47-55: hyper-synthesis + sigma/nu post-processing.  Returns kernel-layout and dict-layout tensors."""
+        log_sigma, log_nu = self.h_s(z_tilde)
+        if self.spatial_params:
+            sigma = torch.exp(log_sigma)
+            nu = torch.clamp(torch.exp(log_nu), min=self.min_nu, max=self.max_nu)
+            return sigma, nu, sigma, nu
+        sigma_k = torch.exp(log_sigma).mean(dim=(2, 3), keepdim=True)                                   # [B,M,1,1]
+        nu_k = torch.clamp(torch.exp(log_nu).mean(dim=(2, 3), keepdim=True), self.min_nu, self.max_nu)
+        return sigma_k, nu_k, sigma_k.expand_as(like), nu_k.expand_as(like)
+
+    def forward(self, x, quant_mode="noise", noise_y=None, noise_z=None):
+        """noise_y / noise_z (optional, not in the reference): supply the uniform draws for bit-exact parity runs."""
+        if quant_mode not in ("noise", "round"):
+            raise ValueError(f"Unknown quant mode: {quant_mode}")
+        y = self.g_a(x)
+        z = self.h_a(y)
+        # K1 (Gaussian): quantise z + nll_z + per-patch bits in one launch (model.py:45,59)
+        z_tilde, nll_z, bits_z = F_sic.bottleneck(z, self.z_prior.log_sigma, quant=quant_mode, lik="gaussian", noise=noise_z)
+        sigma_k, nu_k, sigma, nu = self._student_params(z_tilde, y)
+        # K1 (Student-t): quantise y + nll_y + per-patch bits in one launch (model.py:44,58)
+        y_tilde, nll_y, bits_y = F_sic.bottleneck(y, sigma_k, nu_k, quant=quant_mode, lik=self.likelihood, noise=noise_y)
+        nll_y._sic_bits, nll_z._sic_bits = bits_y, bits_z
+        if self.training:
+            y_hat = y_tilde                                                 # model.py:62
+        else:
+            y_hat = y_tilde if quant_mode == "round" else torch.round(y)   # round(y) twice in the reference; identical bits
+        x_hat = self.g_s(y_hat)
+        return {"x_hat": x_hat, "nll_y": nll_y, "nll_z": nll_z, "y": y, "y_tilde": y_tilde, "z": z, "z_tilde": z_tilde,
+                "sigma": sigma, "nu": nu}
+
+    # ------------------------------------------------------------------------------------------------ entropy coding
+    @torch.no_grad()
+    def compress(self, x, tail=10):
+        """custom_compress (eval_selfcontained_entropy.py:26-74): same return dict.  One host sync for the whole batch
+        (the reference has four per patch); tables are compact [B,C,L+1] instead of replicated over (h,w)."""
+        was_training = self.training
+        self.eval()
+        try:
+            with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True):
+                out = self(x, quant_mode="round")
+        finally:
+            self.train(was_training)
+        y_q, z_q = out["y_tilde"], out["z_tilde"]
+        B = x.size(0)
+        sym_z, min_z, max_z = F_sic.quantize_indices(z_q, do_round=False, tail=tail)
+        sym_y, min_y, max_y = F_sic.quantize_indices(y_q, do_round=False, tail=tail)
+        ext = torch.stack([min_z, max_z, min_y, max_y]).cpu().numpy()       # the single device->host sync
+        mnz, mxz, mny, mxy = (ext[i] for i in range(4))
+        tab_z = F_sic.build_cdf_tables("gaussian", self.z_prior.log_sigma.detach(), None, B, min_z, max_z, int((mxz - mnz).max()) + 2)
+        sig, nu = self._table_params(out["sigma"], out["nu"])
+        tab_y = F_sic.build_cdf_tables("studentt", sig, nu, B, min_y, max_y, int((mxy - mny).max()) + 2, channels=y_q.size(1))
+        sym_z_h, sym_y_h = sym_z.cpu().numpy(), sym_y.cpu().numpy()
+        tab_z_h = tab_z.cpu().numpy().reshape(B, -1, tab_z.shape[-1])
+        tab_y_h = tab_y.cpu().numpy().reshape(B, -1, tab_y.shape[-1])
+        spr_z = z_q.size(2) * z_q.size(3)
+        spr_y = 1 if self.spatial_params else y_q.size(2) * y_q.size(3)
+        strings = []
+        for b in range(B):
+            zs = F_sic.rans_encode(sym_z_h[b], tab_z_h[b], int(mxz[b] - mnz[b] + 1), spr_z)
+            ys = F_sic.rans_encode(sym_y_h[b], tab_y_h[b], int(mxy[b] - mny[b] + 1), spr_y)
+            strings.append([zs, ys])
+        return {"strings": strings, "shape_y": list(y_q.shape), "shape_z": list(z_q.shape),
+                "min_y": [int(v) for v in mny], "max_y": [int(v) for v in mxy],
+                "min_z": [int(v) for v in mnz], "max_z": [int(v) for v in mxz]}
+
+    def _table_params(self, sigma, nu):
+        if self.spatial_params:
+            return sigma.contiguous().view(-1), nu.contiguous().view(-1)
+        return sigma[:, :, 0, 0].contiguous().view(-1), nu[:, :, 0, 0].contiguous().view(-1)
+
+    @torch.no_grad()
+    def decompress(self, compressed):
+        """custom_decompress (eval_selfcontained_entropy.py:76-123): returns x_hat.clamp(0,1) [B,3,H,W]."""
+        dev = next(self.parameters()).device
+        strings = compressed["strings"]
+        shape_y, shape_z = list(compressed["shape_y"]), list(compressed["shape_z"])
+        B = len(strings)
+        mnz, mxz = np.asarray(compressed["min_z"], np.int32), np.asarray(compressed["max_z"], np.int32)
+        mny, mxy = np.asarray(compressed["min_y"], np.int32), np.asarray(compressed["max_y"], np.int32)
+        to_dev = lambda a: torch.from_numpy(a).to(dev)
+        tab_z = F_sic.build_cdf_tables("gaussian", self.z_prior.log_sigma.detach(), None, B, to_dev(mnz), to_dev(mxz),
+                                       int((mxz - mnz).max()) + 2)
+        tab_z_h = tab_z.cpu().numpy().reshape(B, -1, tab_z.shape[-1])
+        n_z = shape_z[1] * shape_z[2] * shape_z[3]
+        z_hat = np.empty((B, n_z), np.float32)
+        for b in range(B):
+            s = F_sic.rans_decode(strings[b][0], n_z, tab_z_h[b], int(mxz[b] - mnz[b] + 1), shape_z[2] * shape_z[3])
+            z_hat[b] = (s + mnz[b]).astype(np.float32)                       # :97
+        z_hat = to_dev(z_hat).view(B, *shape_z[1:])
+        like = torch.empty(B, *shape_y[1:], device=dev)
+        was_training = self.training
+        self.eval()
+        try:
+            with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True):
+                _, _, sigma, nu = self._student_params(z_hat, like)           # :99-106
+                sig, nu = self._table_params(sigma, nu)
+                tab_y = F_sic.build_cdf_tables("studentt", sig, nu, B, to_dev(mny), to_dev(mxy), int((mxy - mny).max()) + 2,
+                                               channels=shape_y[1])
+                tab_y_h = tab_y.cpu().numpy().reshape(B, -1, tab_y.shape[-1])
+                n_y = shape_y[1] * shape_y[2] * shape_y[3]
+                spr_y = 1 if self.spatial_params else shape_y[2] * shape_y[3]
+                y_hat = np.empty((B, n_y), np.float32)
+                for b in range(B):
+                    s = F_sic.rans_decode(strings[b][1], n_y, tab_y_h[b], int(mxy[b] - mny[b] + 1), spr_y)
+                    y_hat[b] = (s + mny[b]).astype(np.float32)               # :117
+                x_hat = self.g_s(to_dev(y_hat).view(B, *shape_y[1:]))         # :119-120
+        finally:
+            self.train(was_training)
+        return x_hat.clamp(0, 1)                                             # :123
+
+
+def _total_bits(t: torch.Tensor) -> torch.Tensor:
+    """Sum of a nll map; uses the per-patch bit counts that kernel K1 already reduced (deterministically) when the map
+    came out of this package's forward(), else falls back to summing the tensor like the reference (model.py:77)."""
+    bits = getattr(t, "_sic_bits", None)
+    return bits.sum() if bits is not None else t.sum()
+
+
+def rate_distortion_loss(out: Dict[str, torch.Tensor], x, lambda_rd=10000.0, dist="mssim"):
+    """model.py:75-107."""
+    N, C, H, W = x.shape
+    R = (_total_bits(out["nll_y"]) + _total_bits(out["nll_z"])) / (N * H * W)
+    R = torch.clamp(R, min=0.0)
+    if dist == "mse":
+        D = F.mse_loss(out["x_hat"], x)
+    elif dist == "msssim":
+        x_hat = out["x_hat"]
+        if x_hat.shape[2:] != x.shape[2:]:
+            x_hat = F.interpolate(x_hat, size=x.shape[2:], mode="bilinear", align_corners=False)
+        D = 1.0 - multi_scale_ssim(x_hat.clamp(0, 1), x, data_range=1.0,
+                                   scale_weights=torch.tensor([0.3, 0.5, 0.2], device=x.device))
+    else:
+        raise ValueError("dist must be 'mse' or 'msssim'")
+    loss = lambda_rd * D + R
+    return loss, R.detach(), D.detach()

