@@ -41,9 +41,11 @@ def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Zero-initialised scratch, one per (device, stream); kernels leave it zeroed (ticket counters self-reset)."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+def _workspace(device: torch.device, nbytes: int, kind: str = "ticketed") -> torch.Tensor:
+    """Zero-initialised scratch, one per (device, stream, kind).  'ticketed' buffers start with the retire counter of the
+    K1 kernels, which those kernels leave at zero; 'scratch' buffers (GDN backward partials) are overwritten freely and
+    must therefore never be the same allocation."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, kind)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
@@ -186,7 +188,7 @@ class _GDN(torch.autograd.Function):
         dbeta = torch.empty_like(beta_param)
         dgamma = torch.empty_like(gamma_weight)
         nws = lib.sic_gdn_bwd_workspace_bytes(B, C, HW)
-        ws = _workspace(x.device, nws)
+        ws = _workspace(x.device, nws, "scratch")
         with torch.cuda.device(x.device):
             _lib.check(lib.sic_gdn_bwd(_ptr(x), _ptr(g), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, inverse, 0, _ptr(dx),
                                        _ptr(dbeta), _ptr(dgamma), _ptr(ws), ws.numel(), _stream()), "sic_gdn_bwd")

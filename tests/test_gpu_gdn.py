@@ -115,3 +115,15 @@ def test_full_size_site_properties():
     gam = (w.view(-1) ** 2 - 2 ** -18).view(1, -1, 1, 1)
     assert bool((y.abs() * gam.sqrt() < 1.0).all())
     assert torch.equal(F.gdn(x, beta, w, False), y)                              # deterministic
+
+
+def test_gdn_backward_does_not_disturb_rate_reduction():
+    """Regression: GDN backward partials and the K1 retire counter live in different workspaces."""
+    F = _F()
+    x = torch.randn(2, 8, 16, 16, device="cuda", requires_grad=True)
+    b = torch.ones(8, device="cuda", requires_grad=True)
+    w = torch.full((8, 1, 1, 1), 0.3, device="cuda", requires_grad=True)
+    F.gdn(x, b, w).sum().backward()
+    y = torch.randn(2, 8, 16, 16, device="cuda") * 3
+    _, nll, bits = F.bottleneck(y, torch.ones(2, 8, 1, 1, device="cuda"), torch.full((2, 8, 1, 1), 5.0, device="cuda"), quant="round")
+    np.testing.assert_allclose(bits.cpu().numpy(), nll.double().sum(dim=(1, 2, 3)).cpu().numpy(), rtol=2e-6)

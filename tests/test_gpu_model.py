@@ -44,6 +44,9 @@ def test_forward_eval_vs_reference_golden(golden):
     assert frac_equal > 0.995
     np.testing.assert_allclose(out["sigma"].cpu().numpy(), G["eval.sigma"], rtol=2e-2)
     assert abs(float(Rr) - float(G["eval.R"])) < 0.02 * float(G["eval.R"])
+    # the per-patch bit counts attached to the nll maps are the sums of those maps (regression: a GDN backward that ran
+    # earlier on the same stream must not disturb the retire counter of the fused rate reduction)
+    np.testing.assert_allclose(out["nll_y"]._sic_bits.cpu().numpy(), out["nll_y"].double().sum(dim=(1, 2, 3)).cpu().numpy(), rtol=2e-6)
     assert abs(float(D) - float(G["eval.D"])) < 1e-3
 
 
@@ -118,7 +121,6 @@ def test_compress_decompress_round_trip(golden, spatial):
     if spatial:
         torch.manual_seed(0)
         m = sic.CompressionModel(N=16, M=24, spatial_params=True, min_nu=2.0).cuda()
-        TPsd = TP.init_state(16, 24, seed=1)
         with torch.no_grad():
             m.g_a.g_a[14].weight.mul_(40.0); m.h_a.h_a[6].weight.mul_(40.0)
         G = golden("model_small")
