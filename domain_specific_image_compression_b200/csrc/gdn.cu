@@ -21,19 +21,6 @@ constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
 constexpr int kChunk4 = 2048;  // float4 per backward unit (8192 elements)
 
-// n / d for n < 2^31 with one mul-hi (Granlund-Montgomery, as in ATen's IntDivider)
-struct FastDiv {
-    unsigned d, magic, shift;
-    FastDiv() : d(1), magic(0), shift(0) {}
-    explicit FastDiv(unsigned div) : d(div) {
-        for (shift = 0; shift < 32; ++shift)
-            if ((1u << shift) >= d) break;
-        uint64_t one = 1;
-        magic = (unsigned)(((one << 32) * ((one << shift) - d)) / d + 1);
-    }
-    __device__ __forceinline__ unsigned div(unsigned n) const { return (__umulhi(n, magic) + n) >> shift; }
-};
-
 __device__ __forceinline__ void eff_params(const float *__restrict__ beta_param, const float *__restrict__ gamma_weight, int c,
                                            float &beta, float &gamma) {
     float b = __ldg(beta_param + c), w = __ldg(gamma_weight + c);
@@ -50,32 +37,37 @@ __device__ __forceinline__ float gdn1(float x, float beta, float gamma) {
     return INVERSE ? __fmul_rn(x, d) : __fdiv_rn(x, d);
 }
 
+// NCHW vector path: one CTA per (plane, chunk of kChunk4 float4) so that beta/gamma are CTA constants and the only
+// per-vector integer work is one add (the first version divided every vector index by HW/4 and C: 15 of its 30
+// instructions per element were index math, ncu r01).
 template <bool INVERSE>
 __global__ void __launch_bounds__(kThreads) gdn_fwd_vec_kernel(const float4 *__restrict__ x, const float *__restrict__ beta_param,
-                                                               const float *__restrict__ gamma_weight, unsigned n4, FastDiv hw4,
-                                                               FastDiv chan, float4 *__restrict__ y) {
-    const unsigned stride = gridDim.x * kThreads * kUnroll;
-    for (unsigned v0 = blockIdx.x * (kThreads * kUnroll) + threadIdx.x; v0 < n4; v0 += stride) {
+                                                               const float *__restrict__ gamma_weight, int C, int hw4, int chunks,
+                                                               float4 *__restrict__ y) {
+    const int plane = blockIdx.x / chunks;
+    const int chunk = blockIdx.x - plane * chunks;
+    float beta, gamma;
+    eff_params(beta_param, gamma_weight, plane % C, beta, gamma);
+    const int v_begin = chunk * kChunk4, v_end = min(v_begin + kChunk4, hw4);
+    const float4 *xp = x + (long)plane * hw4;
+    float4 *yp = y + (long)plane * hw4;
+    for (int v0 = v_begin + threadIdx.x; v0 < v_end; v0 += kThreads * kUnroll) {
         float4 a[kUnroll];
 #pragma unroll
         for (int k = 0; k < kUnroll; ++k) {
-            unsigned v = v0 + k * kThreads;
-            if (v < n4) a[k] = ldg_stream(x + v);
+            int v = v0 + k * kThreads;
+            if (v < v_end) a[k] = ldg_stream(xp + v);
         }
 #pragma unroll
         for (int k = 0; k < kUnroll; ++k) {
-            unsigned v = v0 + k * kThreads;
-            if (v < n4) {
-                unsigned plane = hw4.div(v);
-                unsigned c = plane - chan.div(plane) * chan.d;
-                float beta, gamma;
-                eff_params(beta_param, gamma_weight, (int)c, beta, gamma);
+            int v = v0 + k * kThreads;
+            if (v < v_end) {
                 float4 o;
                 o.x = gdn1<INVERSE>(a[k].x, beta, gamma);
                 o.y = gdn1<INVERSE>(a[k].y, beta, gamma);
                 o.z = gdn1<INVERSE>(a[k].z, beta, gamma);
                 o.w = gdn1<INVERSE>(a[k].w, beta, gamma);
-                stg_stream(y + v, o);
+                stg_stream(yp + v, o);
             }
         }
     }
@@ -93,34 +85,41 @@ __global__ void __launch_bounds__(kThreads) gdn_fwd_scalar_kernel(const float *_
     }
 }
 
-// channels-last (NHWC) vector path: 4 consecutive elements are 4 consecutive channels (C % 4 == 0)
+// channels-last (NHWC) vector path: 4 consecutive elements are 4 consecutive channels (C % 4 == 0).  blockDim is a multiple
+// of C/4 and every stride is a multiple of blockDim, so a thread keeps ONE channel quad for its whole life: the
+// re-parameterised beta/gamma are hoisted into registers and (backward) the per-channel sums need no atomics.
+struct Quad {
+    float b[4], g[4];
+};
+__device__ __forceinline__ Quad load_quad(const float *__restrict__ beta_param, const float *__restrict__ gamma_weight, int c) {
+    Quad q;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) eff_params(beta_param, gamma_weight, c + j, q.b[j], q.g[j]);
+    return q;
+}
+
 template <bool INVERSE>
 __global__ void __launch_bounds__(kThreads) gdn_fwd_nhwc_kernel(const float4 *__restrict__ x, const float *__restrict__ beta_param,
-                                                                const float *__restrict__ gamma_weight, unsigned n4, FastDiv c4,
+                                                                const float *__restrict__ gamma_weight, unsigned n4, int c4,
                                                                 float4 *__restrict__ y) {
-    const unsigned stride = gridDim.x * kThreads * kUnroll;
-    for (unsigned v0 = blockIdx.x * (kThreads * kUnroll) + threadIdx.x; v0 < n4; v0 += stride) {
+    const Quad q = load_quad(beta_param, gamma_weight, (int)(threadIdx.x % c4) * 4);
+    const unsigned stride = gridDim.x * blockDim.x * kUnroll;
+    for (unsigned v0 = blockIdx.x * (blockDim.x * kUnroll) + threadIdx.x; v0 < n4; v0 += stride) {
         float4 a[kUnroll];
 #pragma unroll
         for (int k = 0; k < kUnroll; ++k) {
-            unsigned v = v0 + k * kThreads;
+            unsigned v = v0 + k * blockDim.x;
             if (v < n4) a[k] = ldg_stream(x + v);
         }
 #pragma unroll
         for (int k = 0; k < kUnroll; ++k) {
-            unsigned v = v0 + k * kThreads;
+            unsigned v = v0 + k * blockDim.x;
             if (v < n4) {
-                int c = (int)(v - c4.div(v) * c4.d) * 4;
-                float b0, g0, b1, g1, b2, g2, b3, g3;
-                eff_params(beta_param, gamma_weight, c, b0, g0);
-                eff_params(beta_param, gamma_weight, c + 1, b1, g1);
-                eff_params(beta_param, gamma_weight, c + 2, b2, g2);
-                eff_params(beta_param, gamma_weight, c + 3, b3, g3);
                 float4 o;
-                o.x = gdn1<INVERSE>(a[k].x, b0, g0);
-                o.y = gdn1<INVERSE>(a[k].y, b1, g1);
-                o.z = gdn1<INVERSE>(a[k].z, b2, g2);
-                o.w = gdn1<INVERSE>(a[k].w, b3, g3);
+                o.x = gdn1<INVERSE>(a[k].x, q.b[0], q.g[0]);
+                o.y = gdn1<INVERSE>(a[k].y, q.b[1], q.g[1]);
+                o.z = gdn1<INVERSE>(a[k].z, q.b[2], q.g[2]);
+                o.w = gdn1<INVERSE>(a[k].w, q.b[3], q.g[3]);
                 stg_stream(y + v, o);
             }
         }
@@ -220,6 +219,60 @@ __global__ void __launch_bounds__(kThreads) gdn_bwd_kernel(const float *__restri
     }
 }
 
+// NHWC backward: persistent CTAs, thread-private sums for its channel quad, one smem fold per CTA, partials [C][gridDim.x]
+template <bool INVERSE>
+__global__ void __launch_bounds__(kThreads) gdn_bwd_nhwc_kernel(const float4 *__restrict__ x, const float4 *__restrict__ g,
+                                                                const float *__restrict__ beta_param,
+                                                                const float *__restrict__ gamma_weight, unsigned n4, int C,
+                                                                float4 *__restrict__ dx, float *__restrict__ part) {
+    extern __shared__ float sm[];  // [blockDim.x][8]
+    const int c4 = C >> 2;
+    const int cq = (int)(threadIdx.x % c4);
+    const Quad q = load_quad(beta_param, gamma_weight, cq * 4);
+    float ab[4] = {0.f, 0.f, 0.f, 0.f}, ag[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int U = 2;
+    const unsigned stride = gridDim.x * blockDim.x * U;
+    for (unsigned v0 = blockIdx.x * (blockDim.x * U) + threadIdx.x; v0 < n4; v0 += stride) {
+        float4 xa[U], ga[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            unsigned v = v0 + k * blockDim.x;
+            if (v < n4) { xa[k] = ldg_stream(x + v); ga[k] = ldg_stream(g + v); }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            unsigned v = v0 + k * blockDim.x;
+            if (v < n4) {
+                float4 o;
+                float hb, hg;
+                gdn_bwd1<INVERSE>(xa[k].x, ga[k].x, q.b[0], q.g[0], o.x, hb, hg); ab[0] += hb; ag[0] += hg;
+                gdn_bwd1<INVERSE>(xa[k].y, ga[k].y, q.b[1], q.g[1], o.y, hb, hg); ab[1] += hb; ag[1] += hg;
+                gdn_bwd1<INVERSE>(xa[k].z, ga[k].z, q.b[2], q.g[2], o.z, hb, hg); ab[2] += hb; ag[2] += hg;
+                gdn_bwd1<INVERSE>(xa[k].w, ga[k].w, q.b[3], q.g[3], o.w, hb, hg); ab[3] += hb; ag[3] += hg;
+                stg_stream(dx + v, o);
+            }
+        }
+    }
+    float *mine = sm + threadIdx.x * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mine[j] = ab[j]; mine[4 + j] = ag[j]; }
+    __syncthreads();
+    if ((int)threadIdx.x < c4) {  // fold the blockDim/c4 threads that share this quad, fixed order
+        float sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f};
+        for (unsigned t = threadIdx.x; t < blockDim.x; t += c4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { sb[j] += sm[t * 8 + j]; sg[j] += sm[t * 8 + 4 + j]; }
+        }
+        const long P = gridDim.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            long c = cq * 4 + j;
+            part[c * P + blockIdx.x] = sb[j];
+            part[(long)C * P + c * P + blockIdx.x] = sg[j];
+        }
+    }
+}
+
 // one CTA per channel: fixed-order float64 fold + chain rule through the squared re-parameterisation (layers.py:20-21)
 __global__ void __launch_bounds__(128) gdn_bwd_finalize_kernel(const float *__restrict__ part, const float *__restrict__ beta_param,
                                                                const float *__restrict__ gamma_weight, int C, long P,
@@ -244,6 +297,8 @@ __global__ void __launch_bounds__(128) gdn_bwd_finalize_kernel(const float *__re
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int nhwc_threads(int C) { return (C / 4) * (kThreads / (C / 4)); }  // largest multiple of C/4 that is <= 256
+inline int nhwc_bwd_grid() { return sm_count() * 4; }
 inline int bwd_chunks(int HW) {
     int per = kChunk4 * 4;
     return (HW + per - 1) / per;
@@ -263,19 +318,18 @@ extern "C" int sic_gdn_fwd(const float *x, const float *beta_param, const float 
     const int sms = sm_count();
     const bool al = aligned16(x) && aligned16(y) && n / 4 < (1L << 31);
     if (!channels_last && HW % 4 == 0 && al) {
+        const int hw4 = HW / 4, chunks = (hw4 + kChunk4 - 1) / kChunk4;
+        const long units = (long)B * C * chunks;
+        SIC_CHECK_ARG(units < (1L << 31), "sic_gdn_fwd: too many units");
+        if (inverse) gdn_fwd_vec_kernel<true><<<(unsigned)units, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, C, hw4, chunks, (float4 *)y);
+        else gdn_fwd_vec_kernel<false><<<(unsigned)units, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, C, hw4, chunks, (float4 *)y);
+    } else if (channels_last && C % 4 == 0 && C <= 4 * kThreads && al) {
         unsigned n4 = (unsigned)(n / 4);
-        long want = ((long)n4 + kThreads * kUnroll - 1) / (kThreads * kUnroll);
+        const int c4 = C / 4, threads = nhwc_threads(C);
+        long want = ((long)n4 + threads * kUnroll - 1) / (threads * kUnroll);
         unsigned grid = (unsigned)(want < (long)sms * 8 ? want : (long)sms * 8);
-        FastDiv hw4((unsigned)(HW / 4)), chan((unsigned)C);
-        if (inverse) gdn_fwd_vec_kernel<true><<<grid, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, hw4, chan, (float4 *)y);
-        else gdn_fwd_vec_kernel<false><<<grid, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, hw4, chan, (float4 *)y);
-    } else if (channels_last && C % 4 == 0 && al) {
-        unsigned n4 = (unsigned)(n / 4);
-        long want = ((long)n4 + kThreads * kUnroll - 1) / (kThreads * kUnroll);
-        unsigned grid = (unsigned)(want < (long)sms * 8 ? want : (long)sms * 8);
-        FastDiv c4((unsigned)(C / 4));
-        if (inverse) gdn_fwd_nhwc_kernel<true><<<grid, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, c4, (float4 *)y);
-        else gdn_fwd_nhwc_kernel<false><<<grid, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, c4, (float4 *)y);
+        if (inverse) gdn_fwd_nhwc_kernel<true><<<grid, threads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, c4, (float4 *)y);
+        else gdn_fwd_nhwc_kernel<false><<<grid, threads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, c4, (float4 *)y);
     } else {
         long want = (n + kThreads - 1) / kThreads;
         unsigned grid = (unsigned)(want < (long)sms * 16 ? want : (long)sms * 16);
@@ -288,7 +342,9 @@ extern "C" int sic_gdn_fwd(const float *x, const float *beta_param, const float 
 
 extern "C" size_t sic_gdn_bwd_workspace_bytes(int B, int C, int HW) {
     if (B <= 0 || C <= 0 || HW <= 0) return 0;
-    return (size_t)2 * C * B * bwd_chunks(HW) * sizeof(float);
+    size_t nchw = (size_t)2 * C * B * bwd_chunks(HW) * sizeof(float);
+    size_t nhwc = (size_t)2 * C * nhwc_bwd_grid() * sizeof(float);
+    return nchw > nhwc ? nchw : nhwc;
 }
 
 extern "C" int sic_gdn_bwd(const float *x, const float *g, const float *beta_param, const float *gamma_weight, int B, int C,
@@ -296,19 +352,33 @@ extern "C" int sic_gdn_bwd(const float *x, const float *g, const float *beta_par
                            void *workspace, size_t workspace_bytes, void *stream) {
     SIC_CHECK_ARG(B > 0 && C > 0 && HW > 0, "sic_gdn_bwd: empty shape B=%d C=%d HW=%d", B, C, HW);
     SIC_CHECK_ARG(x && g && dx && beta_param && gamma_weight && workspace, "sic_gdn_bwd: null pointer");
-    if (channels_last) {
-        set_error("sic_gdn_bwd: channels_last layout not implemented");
-        return SIC_E_UNSUPPORTED;
-    }
     if (workspace_bytes < sic_gdn_bwd_workspace_bytes(B, C, HW)) {
         set_error("sic_gdn_bwd: workspace %zu < %zu bytes", workspace_bytes, sic_gdn_bwd_workspace_bytes(B, C, HW));
         return SIC_E_WORKSPACE;
     }
+    cudaStream_t st = (cudaStream_t)stream;
+    float *part = static_cast<float *>(workspace);
+    if (channels_last) {
+        const long n = (long)B * C * HW;
+        if (C % 4 != 0 || C > 4 * kThreads || !aligned16(x) || !aligned16(g) || !aligned16(dx) || n / 4 >= (1L << 31)) {
+            set_error("sic_gdn_bwd: channels_last needs C %% 4 == 0, C <= %d and 16-byte aligned tensors", 4 * kThreads);
+            return SIC_E_UNSUPPORTED;
+        }
+        const int threads = nhwc_threads(C);
+        const unsigned n4 = (unsigned)(n / 4);
+        long want = ((long)n4 + threads * 2 - 1) / (threads * 2);
+        const unsigned grid = (unsigned)(want < nhwc_bwd_grid() ? want : nhwc_bwd_grid());
+        const size_t smem = (size_t)threads * 8 * sizeof(float);
+        if (inverse) gdn_bwd_nhwc_kernel<true><<<grid, threads, smem, st>>>((const float4 *)x, (const float4 *)g, beta_param, gamma_weight, n4, C, (float4 *)dx, part);
+        else gdn_bwd_nhwc_kernel<false><<<grid, threads, smem, st>>>((const float4 *)x, (const float4 *)g, beta_param, gamma_weight, n4, C, (float4 *)dx, part);
+        SIC_CHECK_LAUNCH("sic_gdn_bwd (nhwc)");
+        gdn_bwd_finalize_kernel<<<C, 128, 0, st>>>(part, beta_param, gamma_weight, C, (long)grid, dbeta_param, dgamma_weight);
+        SIC_CHECK_LAUNCH("sic_gdn_bwd finalize");
+        return 0;
+    }
     const int chunks = bwd_chunks(HW);
     const long units = (long)B * C * chunks;
     SIC_CHECK_ARG(units < (1L << 31), "sic_gdn_bwd: too many units");
-    cudaStream_t st = (cudaStream_t)stream;
-    float *part = static_cast<float *>(workspace);
     const bool vec = HW % 4 == 0 && aligned16(x) && aligned16(g) && aligned16(dx);
     if (inverse) {
         if (vec) gdn_bwd_kernel<true, true><<<(unsigned)units, kThreads, 0, st>>>(x, g, beta_param, gamma_weight, C, HW, chunks, dx, part);

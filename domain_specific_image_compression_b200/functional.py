@@ -33,6 +33,17 @@ def _require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.contiguous()
 
 
+def _dense_layout(t: torch.Tensor, name: str):
+    """Returns (tensor, channels_last flag) without copying when `t` is dense in either NCHW or NHWC order."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.SicError(f"{name}: expected a CUDA tensor — this package has no CPU path (the CPU oracle is oracle/, test only)")
+    if t.dtype != torch.float32:
+        raise _lib.SicError(f"{name}: expected float32, got {t.dtype}")
+    if t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last):
+        return t, 1
+    return t.contiguous(), 0
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -163,38 +174,45 @@ class _GDN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, beta_param, gamma_weight, inverse: bool):
         lib = _lib.load()
-        x = _require_cuda_f32(x, "x")
+        x, cl = _dense_layout(x, "x")
+        back_to_cl = False
+        if cl and x.shape[1] % 4 != 0:                # NHWC kernels walk channel quads; odd channel counts go through NCHW
+            x, cl, back_to_cl = x.contiguous(), 0, True
         beta_param = _require_cuda_f32(beta_param, "beta")
-        gamma_weight = _require_cuda_f32(gamma_weight, "gamma_conv.weight")
+        ctx.w_shape = gamma_weight.shape
+        gamma_weight = _require_cuda_f32(gamma_weight.reshape(-1), "gamma_conv.weight")
         B, C = x.shape[0], x.shape[1]
         if beta_param.numel() != C or gamma_weight.numel() != C:
             raise _lib.SicError(f"GDN parameters have {beta_param.numel()}/{gamma_weight.numel()} entries for {C} channels")
         HW = x.numel() // (B * C)
-        y = torch.empty_like(x)
+        y = torch.empty_like(x)                       # keeps x's memory format (NCHW or channels_last)
         with torch.cuda.device(x.device):
-            _launch(lib.sic_gdn_fwd(_ptr(x), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, int(inverse), 0, _ptr(y), _stream()),
+            _launch(lib.sic_gdn_fwd(_ptr(x), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, int(inverse), cl, _ptr(y), _stream()),
                     "sic_gdn_fwd")
         ctx.save_for_backward(x, beta_param, gamma_weight)
-        ctx.cfg = (B, C, HW, int(inverse))
-        return y
+        ctx.cfg = (B, C, HW, int(inverse), cl)
+        return y.contiguous(memory_format=torch.channels_last) if back_to_cl else y
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
         x, beta_param, gamma_weight = ctx.saved_tensors
-        B, C, HW, inverse = ctx.cfg
-        g = _require_cuda_f32(g, "grad_output")
+        B, C, HW, inverse, cl = ctx.cfg
+        if cl:                                        # the gradient must be walked in x's memory order
+            g = _dense_layout(g.contiguous(memory_format=torch.channels_last), "grad_output")[0]
+        else:
+            g = _require_cuda_f32(g, "grad_output")
         dx = torch.empty_like(x)
         dbeta = torch.empty_like(beta_param)
         dgamma = torch.empty_like(gamma_weight)
         nws = lib.sic_gdn_bwd_workspace_bytes(B, C, HW)
         ws = _workspace(x.device, nws, "scratch")
         with torch.cuda.device(x.device):
-            _lib.check(lib.sic_gdn_bwd(_ptr(x), _ptr(g), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, inverse, 0, _ptr(dx),
+            _lib.check(lib.sic_gdn_bwd(_ptr(x), _ptr(g), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, inverse, cl, _ptr(dx),
                                        _ptr(dbeta), _ptr(dgamma), _ptr(ws), ws.numel(), _stream()), "sic_gdn_bwd")
         global launch_count
         launch_count += 2
-        return dx, dbeta, dgamma, None
+        return dx, dbeta, dgamma.view(ctx.w_shape), None
 
 
 def gdn(x: torch.Tensor, beta_param: torch.Tensor, gamma_weight: torch.Tensor, inverse: bool = False) -> torch.Tensor:

@@ -21,7 +21,19 @@ import torch.distributed as dist
 
 
 def _is_dead(name: str) -> bool:
-    return name.endswith(".gamma")            # GDN's stored-but-unused CxC matrix
+    return name == "gamma" or name.endswith(".gamma")     # GDN's stored-but-unused CxC matrix (layers.py:13)
+
+
+def _flat_in_param_order(g: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+    """Flatten a gradient in the MEMORY order of its parameter (the order the flat buffer stores the parameter in)."""
+    if _is_dense_permutation(p):
+        return g.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(-1)
+    return g.reshape(-1)
+
+
+def _is_dense_permutation(p: torch.Tensor) -> bool:
+    """True for non-contiguous tensors that still cover numel() distinct elements of one block (e.g. channels_last)."""
+    return (not p.is_contiguous()) and p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last)
 
 
 class FlatTrainer:
@@ -40,8 +52,9 @@ class FlatTrainer:
         off = 0
         for p in self.live:                    # re-seat every parameter as a view into the flat buffer
             n = p.numel()
-            self.flat[off:off + n].copy_(p.detach().reshape(-1))
-            p.data = self.flat[off:off + n].view_as(p)
+            view = self.flat[off:off + n].as_strided(p.size(), p.stride()) if _is_dense_permutation(p) else self.flat[off:off + n].view_as(p)
+            view.copy_(p.detach())             # keeps a channels_last weight channels_last inside the flat buffer
+            p.data = view
             off += n
         self.flat.requires_grad_(True)
         if self.world > 1:                     # identical replicas: rank 0's weights win
@@ -55,7 +68,7 @@ class FlatTrainer:
         missing = [n for n, p in zip(self.names, self.live) if p.grad is None]
         if missing:
             raise RuntimeError(f"parameters without gradient after backward: {missing[:4]}...")
-        return torch.cat([p.grad.reshape(-1) for p in self.live])
+        return torch.cat([_flat_in_param_order(p.grad, p) for p in self.live])
 
     def reduce_clip_step(self, flat_grad: torch.Tensor) -> torch.Tensor:
         """all-reduce (mean) -> global-norm clip (torch.nn.utils.clip_grad_norm_ semantics, train.py:200-202) -> Adam.

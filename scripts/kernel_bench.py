@@ -1,0 +1,85 @@
+"""Kernel microbenchmark (BASELINE.json configs[4]): Student-t likelihood + rate kernel sweep, latent sizes 16x16x192 ...
+128x128x320, plus the GDN sites of the training step; CUDA-event timing with an L2 flush between launches.
+
+    python scripts/kernel_bench.py [--quick] [--only k1|gdn] [--json out.json]
+Bytes are the ALGORITHMIC bytes of SURVEY.md 8(d) / BASELINE.md 3."""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from domain_specific_image_compression_b200 import functional as F
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--quick", action="store_true")
+ap.add_argument("--only", default="")
+ap.add_argument("--json", default="")
+ap.add_argument("--reps", type=int, default=10)
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+except OSError:
+    PEAK = 6650.0
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+def time_it(fn, reps=args.reps):
+    for _ in range(3): fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2] * 1e-3
+
+rows = []
+def report(name, shape, nbytes, t):
+    r = {"kernel": name, "shape": list(shape), "elems": int(torch.Size(shape).numel()), "alg_bytes": nbytes, "us": t * 1e6, "gbs": nbytes / t / 1e9,
+         "frac_of_measured_hbm_peak": nbytes / t / 1e9 / PEAK}
+    rows.append(r)
+    print(f"{name:34s} {str(tuple(shape)):24s} {t*1e6:9.1f} us {r['gbs']:8.1f} GB/s  {100*r['frac_of_measured_hbm_peak']:5.1f}% of {PEAK:.0f}", flush=True)
+
+if args.only in ("", "k1"):
+    sweep = [(C, h, w) for (C, h, w) in [(192, 16, 16), (192, 32, 32), (320, 32, 32), (192, 64, 64), (320, 64, 64), (320, 128, 128)]]
+    batches = [16] if args.quick else [1, 16, 64]
+    for B in batches:
+        for (C, h, w) in sweep:
+            n = B * C * h * w
+            if n * 4 * 6 > 60e9: continue
+            y = torch.randn(B, C, h, w, device=dev) * 3
+            sg = torch.exp(torch.randn(B, C, 1, 1, device=dev)); nu = torch.exp(torch.randn(B, C, 1, 1, device=dev) + 1.5)
+            report("k1_fwd density bcast noise", y.shape, 12 * n, time_it(lambda: F.bottleneck(y, sg, nu, quant="noise")))
+            report("k1_fwd density bcast round", y.shape, 12 * n, time_it(lambda: F.bottleneck(y, sg, nu, quant="round")))
+            yr = y.clone().requires_grad_(True); sr = sg.clone().requires_grad_(True); nr = nu.clone().requires_grad_(True)
+            yt, nll, bits = F.bottleneck(yr, sr, nr, quant="noise")
+            gb = torch.ones_like(bits); gy = torch.randn_like(yt)
+            report("k1_bwd density bcast (bits+dy~)", y.shape, 12 * n, time_it(lambda: torch.autograd.grad((bits, yt), (yr, sr, nr), (gb, gy), retain_graph=True)))
+            if B == 16 or args.quick:
+                ss = sg.expand_as(y).contiguous(); ns = nu.expand_as(y).contiguous()
+                report("k1_fwd density spatial noise", y.shape, 20 * n, time_it(lambda: F.bottleneck(y, ss, ns, quant="noise")))
+                try:
+                    report("k1_fwd cdf_diff bcast noise", y.shape, 12 * n, time_it(lambda: F.bottleneck(y, sg, nu, quant="noise", lik="cdf_diff")))
+                except Exception as e:
+                    print("cdf_diff unavailable:", str(e)[:80])
+                del ss, ns
+            del y, yr, yt, nll, gy
+
+if args.only in ("", "gdn"):
+    for B, N in ([(16, 128)] if args.quick else [(16, 128), (64, 192)]):
+        for hw in (256, 128, 64, 32):
+            for fmt, tag in ((torch.contiguous_format, "nchw"), (torch.channels_last, "nhwc")):
+                x = torch.randn(B, N, hw, hw, device=dev).contiguous(memory_format=fmt)
+                g = torch.randn(B, N, hw, hw, device=dev).contiguous(memory_format=fmt)
+                beta = torch.sqrt(torch.rand(N, device=dev) + 0.5).requires_grad_(True)
+                w = torch.sqrt(torch.rand(N, 1, 1, 1, device=dev) * 0.3 + 0.01).requires_grad_(True)
+                n = x.numel()
+                for inv in (False, True):
+                    nm = "igdn" if inv else "gdn"
+                    report(f"{nm}_fwd {tag}", x.shape, 8 * n, time_it(lambda: F.gdn(x, beta, w, inv)))
+                    xr = x.clone().requires_grad_(True)
+                    yv = F.gdn(xr, beta, w, inv)
+                    report(f"{nm}_bwd {tag}", x.shape, 12 * n, time_it(lambda: torch.autograd.grad(yv, (xr, beta, w), g, retain_graph=True)))
+                    del xr, yv
+                del x, g
+if args.json:
+    json.dump({"peak_gbs": PEAK, "rows": rows}, open(args.json, "w"), indent=1)

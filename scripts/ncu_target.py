@@ -1,0 +1,35 @@
+"""Minimal launcher for ncu: each hot kernel at its roofline size (what kernel_bench.py quotes)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from domain_specific_image_compression_b200 import functional as F
+dev = torch.device("cuda", 0)
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+if which in ("all", "k1"):
+    y = torch.randn(16, 320, 128, 128, device=dev) * 3
+    sg = torch.exp(torch.randn(16, 320, 1, 1, device=dev)); nu = torch.exp(torch.randn(16, 320, 1, 1, device=dev) + 1.5)
+    for _ in range(reps):
+        F.bottleneck(y, sg, nu, quant="noise")
+        F.bottleneck(y, sg, nu, quant="round")
+    yr = y.clone().requires_grad_(True); sr = sg.clone().requires_grad_(True); nr = nu.clone().requires_grad_(True)
+    yt, nll, bits = F.bottleneck(yr, sr, nr, quant="noise")
+    for _ in range(reps):
+        torch.autograd.grad((bits, yt), (yr, sr, nr), (torch.ones_like(bits), torch.ones_like(yt)), retain_graph=True)
+    if os.environ.get("CDF"):
+        for _ in range(reps):
+            F.bottleneck(y, sg, nu, quant="noise", lik="cdf_diff")
+    del y, yr, yt, nll
+if which in ("all", "gdn"):
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        x = torch.randn(16, 128, 256, 256, device=dev).contiguous(memory_format=fmt)
+        g = torch.randn(16, 128, 256, 256, device=dev).contiguous(memory_format=fmt)
+        beta = torch.sqrt(torch.rand(128, device=dev) + 0.5).requires_grad_(True)
+        w = torch.sqrt(torch.rand(128, 1, 1, 1, device=dev) * 0.3 + 0.01).requires_grad_(True)
+        xr = x.clone().requires_grad_(True)
+        for _ in range(reps):
+            yv = F.gdn(xr, beta, w, False)
+            torch.autograd.grad(yv, (xr, beta, w), g)
+        del x, g, xr, yv
+torch.cuda.synchronize()
+print("ok")

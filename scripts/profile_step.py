@@ -36,7 +36,8 @@ if which in ("both", "ours"):
     model = sic.CompressionModel(N=cfg["N"], M=cfg["M"], min_nu=2.0).to(dev).train()
     with torch.no_grad():
         model.g_a.g_a[14].weight.mul_(40.0); model.h_a.h_a[6].weight.mul_(40.0); model.h_s.mlp_nu[2].bias.add_(1.5)
-    if os.environ.get("CHANNELS_LAST"): model = model.to(memory_format=torch.channels_last)
+    if os.environ.get("CHANNELS_LAST"):
+        model = model.to(memory_format=torch.channels_last); x = x.contiguous(memory_format=torch.channels_last)
     tr = FlatTrainer(model)
     def closure():
         out = model(x, "noise"); return sic.rate_distortion_loss(out, x, 10000.0, "msssim")[0]

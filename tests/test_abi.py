@@ -31,7 +31,7 @@ def test_header_symbols_exported_and_bound():
 def test_workspace_size_queries_are_pure_host_calls():
     lib = _lib.load()
     assert lib.sic_bottleneck_workspace_bytes(16, 192, 256) >= 256 + 3 * 4 * 16 * 192 * 2
-    assert lib.sic_gdn_bwd_workspace_bytes(16, 128, 65536) == 2 * 128 * 16 * 8 * 4
+    assert lib.sic_gdn_bwd_workspace_bytes(16, 128, 65536) >= 2 * 128 * 16 * 8 * 4
     assert lib.sic_bottleneck_workspace_bytes(0, 1, 1) == 256
 
 

@@ -232,3 +232,92 @@ def test_full_size_properties(B, C, h, w):
     sl = (slice(0, 1), slice(0, 8))
     ref = R.studentt_nll_f64(yt[sl].cpu().numpy(), sig[sl].cpu().numpy(), nu[sl].cpu().numpy())
     assert_nll_close(nll[sl].cpu().numpy(), ref)
+
+
+# ------------------------------------------------------------------------------------------------ L2: cdf_diff likelihood
+def _cdf_case(rng, shape, spatial):
+    B, C = shape[:2]
+    pshape = shape if spatial else (B, C, 1, 1)
+    sig = np.exp(rng.uniform(np.log(2e-2), np.log(50.0), pshape)).astype(np.float32)
+    nu = np.exp(rng.uniform(np.log(2.0), np.log(100.0), pshape)).astype(np.float32)
+    y = (rng.standard_t(3, shape) * sig * rng.choice([1.0, 4.0], shape)).astype(np.float32)
+    return y, sig, nu
+
+
+@pytest.mark.parametrize("spatial", [False, True])
+def test_cdfdiff_forward_vs_scipy(spatial):
+    """P = T_nu(y+1/2) - T_nu(y-1/2) (north_star); oracle: scipy float64 same-side survival differences."""
+    F = _F()
+    rng = np.random.default_rng(11 + spatial)
+    y, sig, nu = _cdf_case(rng, (3, 12, 8, 8), spatial)
+    for quant, yq in (("none", y), ("round", R.quantize_round(y))):
+        yt, nll, bits = F.bottleneck(dev(y), dev(sig), dev(nu), quant=quant, lik="cdf_diff")
+        ref = R.studentt_cdfdiff_nll_f64(yq, sig, nu)
+        assert_nll_close(nll.cpu().numpy(), ref)
+        np.testing.assert_allclose(bits.cpu().numpy(), ref.sum(axis=(1, 2, 3)), rtol=1e-5)
+    # probabilities of the integer support sum to one (the table property the coder relies on)
+    k = np.arange(-3000, 3001, dtype=np.float32).reshape(1, 1, -1, 1)
+    _, nll, _ = F.bottleneck(dev(np.broadcast_to(k, (1, 3, 6001, 1)).copy()), dev(np.array([0.3, 1.0, 7.0], np.float32).reshape(1, 3, 1, 1)),
+                             dev(np.array([2.0, 5.0, 40.0], np.float32).reshape(1, 3, 1, 1)), quant="none", lik="cdf_diff")
+    total = torch.exp2(-nll.double()).sum(dim=2).view(-1).cpu().numpy()
+    # nu=2, sigma=0.3: the mass beyond +-3000 is (sigma/3000)^2 ~ 1e-8; fp32 accumulation of 6001 terms dominates
+    assert np.abs(total - 1.0).max() < 1e-5, total
+
+
+def test_cdfdiff_extremes_and_clamps():
+    """Far tails (no underflow / cancellation), sigma and nu outside the clamp range, wide bins (sigma << 1)."""
+    F = _F()
+    y = np.array([0.0, 0.4, -0.5, 3.0, 40.0, -250.0, 1e4, 0.0, 2.0, 5.0, -7.0, 300.0], np.float32).reshape(1, 12, 1, 1)
+    sig = np.array([1e-4, 1e-3, 0.05, 0.3, 1.0, 2.0, 5.0, 2e3, 1e3, 0.7, 12.0, 0.9], np.float32).reshape(1, 12, 1, 1)
+    nu = np.array([1.5, 2.0, 3.0, 100.0, 150.0, 2.5, 2.0, 7.0, 30.0, 80.0, 2.0, 60.0], np.float32).reshape(1, 12, 1, 1)
+    _, nll, _ = F.bottleneck(dev(y), dev(sig), dev(nu), quant="none", lik="cdf_diff")
+    ref = R.studentt_cdfdiff_nll_f64(y, sig, nu)
+    got = nll.cpu().numpy().astype(np.float64)
+    assert np.isfinite(got).all()
+    assert (np.abs(got - ref) <= 2e-4 + 2e-5 * np.abs(ref)).all(), (got.ravel(), ref.ravel())
+
+
+@pytest.mark.parametrize("spatial", [False, True])
+def test_cdfdiff_backward_vs_float64_finite_differences(spatial):
+    F = _F()
+    rng = np.random.default_rng(21 + spatial)
+    shape = (2, 6, 4, 4)
+    y, sig, nu = _cdf_case(rng, shape, spatial)
+    nu = np.clip(nu, 2.05, 95.0).astype(np.float32)                      # keep away from the clamp kinks for the FD reference
+    g = rng.standard_normal(shape).astype(np.float32)
+    yd, sd, nd = dev(y).requires_grad_(True), dev(sig).requires_grad_(True), dev(nu).requires_grad_(True)
+    _, nll, _ = F.bottleneck(yd, sd, nd, quant="none", lik="cdf_diff")
+    (nll * dev(g)).sum().backward()
+    f = lambda yy, ss, nn: R.studentt_cdfdiff_nll_f64(yy, ss, nn)
+    y64, s64, n64 = y.astype(np.float64), sig.astype(np.float64), nu.astype(np.float64)
+    e = 1e-5
+    dx = g * (f(y64 + e, s64, n64) - f(y64 - e, s64, n64)) / (2 * e)
+    ds = g * (f(y64, s64 * (1 + e), n64) - f(y64, s64 * (1 - e), n64)) / (2 * e * s64)
+    dn = g * (f(y64, s64, n64 * (1 + e)) - f(y64, s64, n64 * (1 - e))) / (2 * e * n64)
+    if not spatial:
+        ds, dn = ds.sum((2, 3), keepdims=True), dn.sum((2, 3), keepdims=True)
+    np.testing.assert_allclose(yd.grad.cpu().numpy(), dx, rtol=2e-3, atol=2e-4 * np.abs(dx).max())
+    np.testing.assert_allclose(sd.grad.cpu().numpy(), ds, rtol=2e-3, atol=2e-4 * np.abs(ds).max())
+    np.testing.assert_allclose(nd.grad.cpu().numpy(), dn, rtol=5e-3, atol=5e-4 * np.abs(dn).max())
+
+
+def test_cdfdiff_model_mode_trains(golden):
+    """CompressionModel(likelihood='cdf_diff'): forward/backward runs, rate is >= 0 by construction (a probability mass,
+    unlike the density rate which can go negative: SURVEY D1) and close to the density rate when sigma is not small."""
+    import domain_specific_image_compression_b200 as sic
+    G = golden("model_small")
+    sd = {k[3:]: torch.from_numpy(G[k]) for k in G.files if k.startswith("sd.")}
+    x = torch.from_numpy(G["x"]).cuda()
+    rates = {}
+    for lik in ("density", "cdf_diff"):
+        m = sic.CompressionModel(N=16, M=24, min_nu=2.0, likelihood=lik).cuda()
+        m.load_state_dict(sd)
+        m.train()
+        out = m(x, "noise", noise_y=torch.from_numpy(G["train.noise_y"]).cuda(), noise_z=torch.from_numpy(G["train.noise_z"]).cuda())
+        loss, Rr, D = sic.rate_distortion_loss(out, x, 100.0, "mse")
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() for n, p in m.named_parameters() if p.grad is not None)
+        rates[lik] = float(Rr)
+        if lik == "cdf_diff":
+            assert float(out["nll_y"].min()) >= 0.0
+    assert abs(rates["cdf_diff"] - rates["density"]) < 0.25 * rates["density"]

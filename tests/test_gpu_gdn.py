@@ -127,3 +127,29 @@ def test_gdn_backward_does_not_disturb_rate_reduction():
     y = torch.randn(2, 8, 16, 16, device="cuda") * 3
     _, nll, bits = F.bottleneck(y, torch.ones(2, 8, 1, 1, device="cuda"), torch.full((2, 8, 1, 1), 5.0, device="cuda"), quant="round")
     np.testing.assert_allclose(bits.cpu().numpy(), nll.double().sum(dim=(1, 2, 3)).cpu().numpy(), rtol=2e-6)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", [(2, 128, 24, 20), (3, 192, 9, 7), (2, 16, 5, 5), (1, 320, 8, 8), (2, 6, 4, 4)])
+def test_channels_last_layout_matches_nchw(shape, inverse):
+    """NHWC (torch.channels_last) activations: forward bit-identical to the NCHW path, output keeps the memory format;
+    backward equal to the NCHW backward within the reduction-order tolerance.  C % 4 != 0 falls back to the scalar path."""
+    F = _F()
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    C = shape[1]
+    x = torch.randn(*shape, device="cuda", generator=g) * 3
+    go = torch.randn(*shape, device="cuda", generator=g)
+    beta = torch.sqrt(torch.rand(C, device="cuda", generator=g) + 0.5)
+    w = torch.sqrt(torch.rand(C, 1, 1, 1, device="cuda", generator=g) * 0.3 + 0.01)
+    res = []
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        xi = x.clone().contiguous(memory_format=fmt).requires_grad_(True)
+        bi, wi = beta.clone().requires_grad_(True), w.clone().requires_grad_(True)
+        y = F.gdn(xi, bi, wi, inverse)
+        assert y.is_contiguous(memory_format=fmt)
+        (y * go).sum().backward()
+        res.append((y.detach(), xi.grad, bi.grad, wi.grad))
+    assert torch.equal(res[0][0], res[1][0])
+    assert res[1][1].is_contiguous(memory_format=torch.channels_last)
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-7

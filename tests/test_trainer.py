@@ -1,0 +1,100 @@
+"""FlatTrainer host logic on CPU: equivalence with the reference's step (zero_grad / backward / clip_grad_norm_ / Adam,
+train.py:195-204) and, with world_size 2 over gloo, with a single-process step on the concatenated batch."""
+import copy
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from domain_specific_image_compression_b200.trainer import FlatTrainer
+
+
+class Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Conv2d(3, 8, 3, padding=1)
+        self.b = torch.nn.Conv2d(8, 4, 3, padding=1)
+        self.gamma = torch.nn.Parameter(torch.eye(4))      # dead parameter, like GDN's CxC gamma: never receives a gradient
+
+    def forward(self, x):
+        return self.b(torch.relu(self.a(x)))
+
+
+def _loss(m, x):
+    return (m(x) - 0.3).square().mean() * 50.0
+
+
+def test_flat_trainer_equals_reference_step():
+    torch.manual_seed(0)
+    m = Toy()
+    ref = copy.deepcopy(m)
+    tr = FlatTrainer(m, lr=1e-2, grad_clip=1.0, fused=False)
+    assert "gamma" not in tr.names and tr.flat.numel() == sum(p.numel() for n, p in ref.named_parameters() if n != "gamma")
+    opt = torch.optim.Adam([p for n, p in ref.named_parameters() if n != "gamma"], lr=1e-2)
+    x = torch.rand(4, 3, 8, 8)
+    for _ in range(4):
+        tr.step(lambda: _loss(m, x))
+        opt.zero_grad(set_to_none=True)
+        _loss(ref, x).backward()
+        torch.nn.utils.clip_grad_norm_([p for n, p in ref.named_parameters() if n != "gamma"], 1.0)
+        opt.step()
+    for (n, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        assert torch.allclose(p, q, atol=1e-7), n
+    # parameters are views into the flat buffer: an optimizer step on the buffer is visible in the module
+    assert m.a.weight.data_ptr() == tr.flat.data_ptr()
+
+
+def test_missing_gradient_is_reported():
+    m = Toy()
+    tr = FlatTrainer(m, fused=False)
+    with pytest.raises(RuntimeError):
+        tr.step(lambda: m.a(torch.rand(1, 3, 4, 4)).sum())      # m.b gets no gradient
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                  # different initial weights per rank: the broadcast must fix that
+    m = Toy()
+    tr = FlatTrainer(m, lr=1e-2, grad_clip=0.5, fused=False)
+    g = torch.Generator().manual_seed(7)
+    x_all = torch.rand(4, 3, 8, 8, generator=g)
+    x = x_all[rank * 2:(rank + 1) * 2]             # patches shard across ranks
+    for _ in range(3):
+        tr.step(lambda: _loss(m, x))
+    q.put((rank, tr.flat.detach().numpy().copy()))      # by value: the worker may exit before the parent reads
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_gloo_equal_single_process_on_full_batch():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got = {k: torch.from_numpy(v) for k, v in got.items()}
+    assert torch.equal(got[0], got[1])             # replicas stay identical
+    torch.manual_seed(100)                         # rank 0's initial weights
+    m = Toy()
+    tr = FlatTrainer(m, lr=1e-2, grad_clip=0.5, fused=False)
+    x_all = torch.rand(4, 3, 8, 8, generator=torch.Generator().manual_seed(7))
+    for _ in range(3):
+        tr.step(lambda: _loss(m, x_all))           # mean over 4 patches == mean of the two ranks' means over 2 patches
+    assert torch.allclose(tr.flat.detach(), got[0], atol=2e-6)
