@@ -27,6 +27,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_REAL_STDOUT = sys.stdout
 
 CONFIGS = {
     # BASELINE.json configs[1]: full training step batch 16 fp32 on 1xB200 (N=128, M=192)
@@ -51,7 +52,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nchw", action="store_true", help="keep activations NCHW (default: torch.channels_last, which saves cuDNN's "
                     "internal NCHW<->NHWC transposes; GDN kernels run natively in either layout)")
-    ap.add_argument("--cudnn-benchmark", action="store_true")
+    ap.add_argument("--no-cudnn-benchmark", action="store_true", help="cuDNN autotune is on by default (warm-up steps absorb it)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph")
     return ap.parse_args()
 
 
@@ -104,7 +106,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 def workload_name(args, cfg):
@@ -174,6 +176,10 @@ def run_ours(args):
 
     cfg = CONFIGS[args.config]
     B, H, W = cfg["batch"], cfg["H"], cfg["W"]
+    # kernel rooflines first: they draw from torch's CUDA generator, which must not be touched between graph replays
+    roof, kernels = kernel_rooflines(cfg, dev) if rank == 0 else (None, None)
+    if world > 1:
+        dist.barrier()
     torch.manual_seed(42)                                      # config.py:32
     model = sic.CompressionModel(N=cfg["N"], M=cfg["M"], spatial_params=False, min_nu=2.0, max_nu=100.0).to(dev)
     with torch.no_grad():                                      # 'spread' init so latents are not all zero
@@ -181,8 +187,7 @@ def run_ours(args):
         model.h_a.h_a[6].weight.mul_(40.0)
         model.h_s.mlp_nu[2].bias.add_(1.5)
     model.train()
-    if args.cudnn_benchmark:
-        torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     fmt = torch.contiguous_format if args.nchw else torch.channels_last
     model = model.to(memory_format=fmt)
     trainer = FlatTrainer(model, lr=1e-4, betas=(0.9, 0.999), grad_clip=1.0)
@@ -198,13 +203,29 @@ def run_ours(args):
             return loss
         return closure
 
-    def step_resident():
-        return trainer.step(closure_on(x_dev))
+    graph_note = "eager launches"
+    run_static = None
+    x_stage.copy_(x_dev)
+    launches_per_step = None
+    if not args.no_graph:
+        try:
+            n_cap = max(3, args.warmup)
+            lc0 = F_sic.launch_count
+            run_static = trainer.capture(closure_on(x_stage), warmup=n_cap)
+            launches_per_step = (F_sic.launch_count - lc0) // (n_cap + 1)     # our kernels recorded per replayed step
+            graph_note = "whole step (zero_grad..Adam, incl. the all-reduce) replayed as one CUDA graph"
+        except Exception as e:                                   # fall back loudly, never silently
+            print(f"[bench] CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}", file=sys.stderr)
+            run_static = None
+    x_stage.copy_(x_dev)
+
+    def step_resident():                                         # inputs already resident in HBM (x_stage holds the batch)
+        return run_static() if run_static is not None else trainer.step(closure_on(x_stage))
 
     def step_e2e():
-        x_stage.copy_(x_host, non_blocking=True)               # H2D of this step's patches (pinned)
-        loss = trainer.step(closure_on(x_stage))
-        loss_host.copy_(loss, non_blocking=False)               # D2H of the step's result
+        x_stage.copy_(x_host, non_blocking=True)                 # H2D of this step's patches (pinned)
+        loss = run_static() if run_static is not None else trainer.step(closure_on(x_stage))
+        loss_host.copy_(loss, non_blocking=False)                # D2H of the step's result
         return loss_host
 
     def barrier():
@@ -233,7 +254,7 @@ def run_ours(args):
         sampler.start()
     l0 = F_sic.launch_count
     ms_total = timed(step_resident, K)
-    launches = F_sic.launch_count - l0
+    launches = F_sic.launch_count - l0 if run_static is None else launches_per_step * K
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
@@ -241,7 +262,6 @@ def run_ours(args):
     value = B * world * K / (ms_total / 1e3)
     e2e_value = B * world * K / (ms_e2e / 1e3)
 
-    roof, kernels = kernel_rooflines(cfg, dev) if rank == 0 else (None, None)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, ms, cores = cpu_reference(cfg, 1, 1, 4, args.dist)
@@ -254,13 +274,14 @@ def run_ours(args):
             "config": {"workload": workload_name(args, cfg), "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (>= 5 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "conv_math": "cuDNN fp32 with TF32 allowed (PyTorch default, as the reference)",
-                       "activation_layout": "NCHW" if args.nchw else "channels_last"},
+                       "activation_layout": "NCHW" if args.nchw else "channels_last", "launch": graph_note,
+                       "cudnn_benchmark": not args.no_cudnn_benchmark},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base,
             "allreduce_bytes_per_step": trainer.nbytes_allreduce if world > 1 else 0,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -328,6 +349,12 @@ def kernel_rooflines(cfg, dev):
 
 def main():
     args = parse()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on init), so
+    # route fd 1 to stderr for the whole run and keep a private handle on the real stdout for the result line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

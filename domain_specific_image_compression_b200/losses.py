@@ -56,5 +56,8 @@ def multi_scale_ssim(x, y, data_range=1.0, scale_weights=None, kernel_size=11, k
         ssim_last, cs = _ssim_and_cs(x, y, win, c1, c2)
         terms.append(cs)
     stacked = torch.relu(torch.stack(terms[:-1] + [ssim_last], dim=0))          # [levels,B,C]
-    per_image = torch.prod(stacked ** scale_weights.view(-1, 1, 1), dim=0).mean(1)
-    return per_image.mean(0)
+    powered = stacked ** scale_weights.view(-1, 1, 1)
+    per_image = powered[0]
+    for lvl in range(1, levels):              # explicit product: torch.prod's backward synchronises (zero counting),
+        per_image = per_image * powered[lvl]  # which a CUDA-graph capture of the training step does not permit
+    return per_image.mean(1).mean(0)

@@ -156,6 +156,18 @@ class CompressionModel(nn.Module):
         return x_hat.clamp(0, 1)                                             # :123
 
 
+_MSSSIM_WEIGHTS = {}
+
+
+def _msssim_weights(device) -> torch.Tensor:
+    """[0.3, 0.5, 0.2] of model.py:100, created once per device (a host->device copy per call would break graph capture)."""
+    w = _MSSSIM_WEIGHTS.get(device)
+    if w is None:
+        w = torch.tensor([0.3, 0.5, 0.2], device=device)
+        _MSSSIM_WEIGHTS[device] = w
+    return w
+
+
 def _total_bits(t: torch.Tensor) -> torch.Tensor:
     """Sum of a nll map; uses the per-patch bit counts that kernel K1 already reduced (deterministically) when the map
     came out of this package's forward(), else falls back to summing the tensor like the reference (model.py:77)."""
@@ -174,8 +186,7 @@ def rate_distortion_loss(out: Dict[str, torch.Tensor], x, lambda_rd=10000.0, dis
         x_hat = out["x_hat"]
         if x_hat.shape[2:] != x.shape[2:]:
             x_hat = F.interpolate(x_hat, size=x.shape[2:], mode="bilinear", align_corners=False)
-        D = 1.0 - multi_scale_ssim(x_hat.clamp(0, 1), x, data_range=1.0,
-                                   scale_weights=torch.tensor([0.3, 0.5, 0.2], device=x.device))
+        D = 1.0 - multi_scale_ssim(x_hat.clamp(0, 1), x, data_range=1.0, scale_weights=_msssim_weights(x.device))
     else:
         raise ValueError("dist must be 'mse' or 'msssim'")
     loss = lambda_rd * D + R

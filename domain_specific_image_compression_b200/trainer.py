@@ -61,7 +61,10 @@ class FlatTrainer:
             dist.broadcast(self.flat.detach(), src=0, group=process_group)
         if fused is None:
             fused = self.flat.is_cuda
-        self.opt = torch.optim.Adam([self.flat], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, fused=fused)
+        # capturable: the step counter lives on the device, so the whole step can be recorded into a CUDA graph
+        self.opt = torch.optim.Adam([self.flat], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, fused=fused,
+                                    capturable=bool(self.flat.is_cuda))
+        self.graph = None
         self.nbytes_allreduce = total * self.flat.element_size()
 
     def pack_grads(self) -> torch.Tensor:
@@ -91,3 +94,27 @@ class FlatTrainer:
         loss.backward()
         self.reduce_clip_step(self.pack_grads())
         return loss.detach()
+
+    def capture(self, loss_closure: Callable[[], torch.Tensor], warmup: int = 3) -> Callable[[], torch.Tensor]:
+        """Record zero_grad + forward + loss + backward + all-reduce + clip + Adam into ONE CUDA graph and return a
+        replay function.  The closure must read its batch from a static tensor (copy the next batch into it before each
+        replay).  The in-kernel Philox offset advances on the device, so every replay draws fresh quantisation noise.
+        Launch-bound inner loops are what graphs are for: the step is ~600 small launches next to a dozen large ones."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):            # cuDNN autotune, workspaces, Philox state: all allocated before capture
+                self.step(loss_closure)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        for p in self.live:
+            p.grad = None
+        with torch.cuda.graph(graph):
+            static_loss = self.step(loss_closure)
+        self.graph = graph
+
+        def replay() -> torch.Tensor:
+            graph.replay()
+            return static_loss
+        return replay
