@@ -27,6 +27,7 @@ SOURCES = [
     ("bottleneck.cu", []),
     ("bottleneck_cdf.cu", []),
     ("gdn.cu", []),
+    ("gdn_dense.cu", []),
     ("tables.cu", ["-fmad=false"]),
     ("rans_host.cpp", []),
 ]

@@ -220,6 +220,58 @@ def gdn(x: torch.Tensor, beta_param: torch.Tensor, gamma_weight: torch.Tensor, i
     return _GDN.apply(x, beta_param, gamma_weight, inverse)
 
 
+class _GDNDense(torch.autograd.Function):
+    """Dense-gamma GDN (G3).  Forward: the tcgen05 kernel.  Backward: the two GEMMs of SURVEY 8(a') G3 through torch.matmul
+    (plain library GEMMs, cuBLAS) on the re-parameterised gamma — the dense path is a capability the reference never runs."""
+
+    @staticmethod
+    def forward(ctx, x, beta_param, gamma_param, inverse: bool):
+        lib = _lib.load()
+        if x.dim() != 4:
+            raise _lib.SicError("dense GDN expects [B,C,H,W]")
+        xc = _dense_layout(x.contiguous(memory_format=torch.channels_last), "x")[0]   # the kernel walks [positions, C]
+        beta_param = _require_cuda_f32(beta_param, "beta")
+        gamma_param = _require_cuda_f32(gamma_param, "gamma")
+        B, C, H, W = x.shape
+        if gamma_param.shape != (C, C) or beta_param.numel() != C:
+            raise _lib.SicError(f"dense GDN parameters {tuple(beta_param.shape)}/{tuple(gamma_param.shape)} do not match C={C}")
+        y = torch.empty_like(xc)
+        with torch.cuda.device(x.device):
+            _launch(lib.sic_gdn_dense_fwd(_ptr(xc), _ptr(beta_param), _ptr(gamma_param), B * H * W, C, int(inverse), _ptr(y),
+                                          _stream()), "sic_gdn_dense_fwd")
+        ctx.save_for_backward(xc, beta_param, gamma_param)
+        ctx.inverse = bool(inverse)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, beta_param, gamma_param = ctx.saved_tensors
+        B, C, H, W = xc.shape
+        X = xc.permute(0, 2, 3, 1).reshape(-1, C)                    # [P, C] view of the channels-last block
+        G = g.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(-1, C)
+        beta = beta_param * beta_param - 2.0 ** -18
+        gamma = gamma_param * gamma_param - 2.0 ** -18
+        X2 = X * X
+        s = torch.addmm(beta, X2, gamma.t())                         # s[p,i] = beta_i + sum_j gamma_ij x2[p,j]
+        d = torch.sqrt(s)
+        if ctx.inverse:
+            h = 0.5 * G * X / d
+            direct = G * d
+        else:
+            h = -0.5 * G * X / (d * s)
+            direct = G / d
+        dX = direct + 2.0 * X * (h @ gamma)                          # dx_j = direct_j + 2 x_j sum_i gamma_ij h_i
+        dgamma = h.t() @ X2                                          # dgamma_ij = sum_p h_i x2_j
+        dbeta = h.sum(0)
+        dx = dX.reshape(B, H, W, C).permute(0, 3, 1, 2)
+        return dx, dbeta * 2.0 * beta_param, dgamma * 2.0 * gamma_param, None
+
+
+def gdn_dense(x: torch.Tensor, beta_param: torch.Tensor, gamma_param: torch.Tensor, inverse: bool = False) -> torch.Tensor:
+    """Dense-gamma GDN/IGDN on tcgen05 tensor cores (G3); returns a channels_last tensor."""
+    return _GDNDense.apply(x, beta_param, gamma_param, inverse)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # K4 / K3 / E1
 def quantize_indices(q: torch.Tensor, do_round: bool = False, tail: int = 10, want_symbols: bool = True):

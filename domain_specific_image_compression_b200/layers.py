@@ -16,8 +16,9 @@ from . import functional as F_sic
 class GDN(nn.Module):
     """y = x / sqrt(beta + gamma * x^2) per channel (inverse: multiply), layers.py:6-27."""
 
-    def __init__(self, channels, inverse=False, beta_min=1e-6, gamma_init=0.1, reparam_offset=2**-18):
+    def __init__(self, channels, inverse=False, beta_min=1e-6, gamma_init=0.1, reparam_offset=2**-18, dense=False):
         super().__init__()
+        self.dense = dense     # True: use the full C x C `gamma` on tensor cores (north_star variant); False: the reference's path
         if reparam_offset != 2**-18:
             raise ValueError("the CUDA kernel fixes reparam_offset at 2**-18 (the reference never passes another value)")
         self.inverse = inverse
@@ -29,6 +30,8 @@ class GDN(nn.Module):
             self.gamma_conv.weight.copy_(self.gamma.diag().view(channels, 1, 1, 1))                        # layers.py:16-17
 
     def forward(self, x):
+        if self.dense:
+            return F_sic.gdn_dense(x, self.beta, self.gamma, self.inverse)
         return F_sic.gdn(x, self.beta, self.gamma_conv.weight, self.inverse)
 
 

@@ -92,6 +92,15 @@ int sic_gdn_bwd(const float *x, const float *g, const float *beta_param, const f
                 int inverse, int channels_last, float *dx, float *dbeta_param, float *dgamma_weight, void *workspace,
                 size_t workspace_bytes, void *stream);
 
+/* G3  GDN / IGDN with a DENSE C x C gamma (north_star's tensor-core contraction; the reference stores the matrix,
+ * layers.py:13, but never uses it: SURVEY.md D3).  s[p,i] = beta_i + sum_j gamma_ij x[p,j]^2, y = x/sqrt(s) | x*sqrt(s).
+ *   x, y: CHANNELS-LAST activations viewed as [positions, C] (positions = B*H*W); beta_param [C] and gamma_param [C,C]
+ *   (row i = output channel) are the stored parameters, re-parameterised inside like layers.py:20-21.
+ *   tcgen05.mma kind::tf32 with an exact hi/lo split of x^2: tolerance-only mode (gamma at TF32 precision).
+ *   This build: C in {32, 64, 96, 128} (operands resident in shared memory), otherwise SIC_E_UNSUPPORTED. */
+int sic_gdn_dense_fwd(const float *x, const float *beta_param, const float *gamma_param, long positions, int C, int inverse,
+                      float *y, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * K4  symbols: eval_selfcontained_entropy.py:39-40,48 / :52-53,62 (per patch, no host sync).
  *   q [B,n_per_patch] float latent; do_round != 0 applies torch.round first.

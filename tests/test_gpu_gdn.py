@@ -153,3 +153,67 @@ def test_channels_last_layout_matches_nchw(shape, inverse):
     assert res[1][1].is_contiguous(memory_format=torch.channels_last)
     for a, b in zip(res[0][1:], res[1][1:]):
         assert float((a - b).abs().max()) <= 1e-5 * float(a.abs().max()) + 1e-7
+
+
+# ------------------------------------------------------------------------------------------------ G3: dense gamma on tcgen05
+def _tf32_trunc(a):
+    return (a.astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", [(2, 128, 16, 24), (1, 64, 9, 7), (3, 32, 5, 5), (2, 96, 12, 12), (1, 128, 1, 3)])
+def test_dense_gdn_forward_vs_oracle(shape, inverse):
+    """tcgen05 kernel vs the float64 oracle (F.conv2d(x^2, gamma, beta) semantics).  gamma is consumed at TF32 precision,
+    so the tight comparison uses the oracle with gamma truncated to TF32; against the untruncated oracle the difference is
+    the documented 2^-11 parameter perturbation."""
+    F = _F()
+    rng = np.random.default_rng(sum(shape) + inverse)
+    B, C, H, W = shape
+    x = (rng.standard_normal(shape) * 2).astype(np.float32)
+    beta_p = np.sqrt(rng.random(C) + 0.5).astype(np.float32)
+    gamma_p = np.sqrt(rng.random((C, C)) * 0.02 + np.eye(C) * 0.1 + 2.0 ** -18).astype(np.float32)
+    y = F.gdn_dense(dev(x), dev(beta_p), dev(gamma_p), inverse)
+    assert y.shape == tuple(shape) and y.is_contiguous(memory_format=torch.channels_last) or min(H, W) == 1 or C == 1
+    beta = (beta_p * beta_p - np.float32(2.0 ** -18)).astype(np.float32)
+    gamma = (gamma_p * gamma_p - np.float32(2.0 ** -18)).astype(np.float32)
+    ref_t = R.gdn_dense_fwd_f64(x, beta, _tf32_trunc(gamma), inverse)
+    ref = R.gdn_dense_fwd_f64(x, beta, gamma, inverse)
+    got = y.cpu().numpy().astype(np.float64)
+    assert np.abs(got - ref_t).max() <= 5e-6 * np.abs(ref_t).max() + 1e-7
+    assert np.abs(got - ref).max() <= 1e-3 * np.abs(ref).max()
+
+
+def test_dense_gdn_equals_diag_path_for_diagonal_gamma():
+    """With a diagonal gamma the dense contraction is the reference's GDN (layers.py:19-27) up to TF32 on gamma."""
+    F = _F()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    C = 128
+    x = torch.randn(2, C, 20, 20, device="cuda", generator=g) * 2
+    beta = torch.sqrt(torch.rand(C, device="cuda", generator=g) + 0.5)
+    w = torch.sqrt(torch.rand(C, device="cuda", generator=g) * 0.3 + 0.01)
+    gamma_p = torch.full((C, C), 2.0 ** -9, device="cuda")          # sqrt(2^-18): off-diagonal re-parameterises to exactly 0
+    gamma_p[torch.arange(C), torch.arange(C)] = w
+    yd = F.gdn_dense(x, beta, gamma_p, False)
+    yr = F.gdn(x, beta, w.view(C, 1, 1, 1), False)
+    assert float((yd - yr).abs().max()) <= 1e-3 * float(yr.abs().max())
+
+
+def test_dense_gdn_backward_and_module():
+    import domain_specific_image_compression_b200 as sic
+    torch.manual_seed(0)
+    m = sic.GDN(64, dense=True).cuda()
+    with torch.no_grad():
+        m.gamma.add_(torch.rand(64, 64, device="cuda") * 0.05)
+    x = (torch.randn(2, 64, 8, 8, device="cuda") * 2).requires_grad_(True)
+    go = torch.randn(2, 64, 8, 8, device="cuda")
+    (m(x) * go).sum().backward()
+    xd = x.detach().double().requires_grad_(True)
+    bd, gd = m.beta.detach().double().requires_grad_(True), m.gamma.detach().double().requires_grad_(True)
+    s = torch.nn.functional.conv2d(xd * xd, (gd * gd - 2.0 ** -18).view(64, 64, 1, 1), bd * bd - 2.0 ** -18)
+    ((xd / torch.sqrt(s)) * go.double()).sum().backward()
+    for mine, ref in ((x.grad, xd.grad), (m.beta.grad, bd.grad), (m.gamma.grad, gd.grad)):
+        assert float((mine.double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-7
+    assert m.gamma_conv.weight.grad is None                       # the diagonal conv is the unused one in dense mode
+    with pytest.raises(sic.SicError):
+        F = _F()
+        F.gdn_dense(torch.randn(1, 192, 4, 4, device="cuda"), torch.ones(192, device="cuda"), torch.ones(192, 192, device="cuda"))
