@@ -253,7 +253,9 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     l0 = F_sic.launch_count
+    torch.cuda.profiler.start()                              # ncu --profile-from-start off isolates the timed region (all threads)
     ms_total = timed(step_resident, K)
+    torch.cuda.profiler.stop()
     launches = F_sic.launch_count - l0 if run_static is None else launches_per_step * K
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):

@@ -25,7 +25,7 @@ namespace sic {
 namespace {
 
 constexpr int kTileM = 128;      // positions per tile == UMMA M == TMEM lanes
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;     // 16 warps: 8 float4 of x per thread for the current tile + 8 prefetched for the next
 constexpr float kOffset = 3.814697265625e-06f;  // 2^-18, layers.py:8
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -131,16 +131,27 @@ __global__ void __launch_bounds__(kThreads, 1) gdn_dense_fwd_kernel(const float 
     uint32_t phase = 0;
 
     const long n_tiles = (P + kTileM - 1) / kTileM;
-    for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long p0 = tile * kTileM;
-        const int valid = (int)min((long)kTileM, P - p0);
-        // ---- load x (coalesced: the tile is one contiguous block), square, split, write A_hi / A_lo swizzled
-        float4 xr[PER_THREAD];
+    // software pipeline: the x tile of the NEXT iteration is requested from HBM before this iteration's MMA/epilogue, so the
+    // load latency (the dominant stall of the first version: ncu long_scoreboard 7.6/issue) hides behind tensor + epilogue work
+    float4 xn[PER_THREAD];
+    auto prefetch = [&](long t) {
+        const long q0 = t * kTileM;
+        const int vld = (int)min((long)kTileM, P - q0);
 #pragma unroll
         for (int k = 0; k < PER_THREAD; ++k) {
             int idx = tid + k * kThreads, r = idx / V;
-            xr[k] = r < valid ? ldg_stream(reinterpret_cast<const float4 *>(x + p0 * C) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xn[k] = (t < n_tiles && r < vld) ? ldg_stream(reinterpret_cast<const float4 *>(x + q0 * C) + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+    };
+    prefetch(blockIdx.x);
+    for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long p0 = tile * kTileM;
+        const int valid = (int)min((long)kTileM, P - p0);
+        // ---- take the prefetched x (coalesced: the tile is one contiguous block), square, split, write A_hi / A_lo swizzled
+        float4 xr[PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < PER_THREAD; ++k) xr[k] = xn[k];
+        prefetch(tile + gridDim.x);
 #pragma unroll
         for (int k = 0; k < PER_THREAD; ++k) {
             int idx = tid + k * kThreads, r = idx / V, c4 = idx - r * V;
@@ -187,13 +198,13 @@ __global__ void __launch_bounds__(kThreads, 1) gdn_dense_fwd_kernel(const float 
         {
             const int lg = warp & 3;                       // TMEM lane group this warp may touch
             const int row = lg * 32 + lane;
-            for (int cb = (warp >> 2) * 32; cb < C; cb += 64) {
+            for (int cb = (warp >> 2) * 32; cb < C; cb += (kThreads / 128) * 32) {
                 float v[32];
                 tmem_ld32(tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)cb, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float s = sBeta[cb + j] + v[j];
-                    v[j] = INVERSE ? sqrtf(s) : rsqrtf(s);
+                    v[j] = INVERSE ? __fsqrt_rn(s) : rsqrtf(s);
                 }
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4)

@@ -81,5 +81,17 @@ if args.only in ("", "gdn"):
                     report(f"{nm}_bwd {tag}", x.shape, 12 * n, time_it(lambda: torch.autograd.grad(yv, (xr, beta, w), g, retain_graph=True)))
                     del xr, yv
                 del x, g
+if args.only in ("", "dense"):
+    for B, N, hw in ([(16, 128, 256)] if args.quick else [(16, 128, 256), (16, 128, 128), (16, 128, 64), (16, 64, 256)]):
+        x = torch.randn(B, N, hw, hw, device=dev).contiguous(memory_format=torch.channels_last)
+        beta = torch.sqrt(torch.rand(N, device=dev) + 0.5)
+        gm = torch.sqrt(torch.rand(N, N, device=dev) * 0.02 + torch.eye(N, device=dev) * 0.1 + 2.0 ** -18)
+        n = x.numel()
+        for inv in (False, True):
+            t = time_it(lambda: F.gdn_dense(x, beta, gm, inv))
+            report(f"{'igdn' if inv else 'gdn'}_dense_fwd tcgen05 nhwc", x.shape, 8 * n, t)
+            rows[-1]["tflops_tf32_2pass"] = 2 * 2 * N * N * (n // N) / t / 1e12
+            print(f"    -> {rows[-1]['tflops_tf32_2pass']:.1f} TFLOP/s of tf32 MMA work (hi+lo passes)")
+        del x
 if args.json:
     json.dump({"peak_gbs": PEAK, "rows": rows}, open(args.json, "w"), indent=1)

@@ -31,5 +31,11 @@ if which in ("all", "gdn"):
             yv = F.gdn(xr, beta, w, False)
             torch.autograd.grad(yv, (xr, beta, w), g)
         del x, g, xr, yv
+if which in ("all", "dense"):
+    x = torch.randn(16, 128, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
+    beta = torch.sqrt(torch.rand(128, device=dev) + 0.5)
+    gm = torch.sqrt(torch.rand(128, 128, device=dev) * 0.02 + torch.eye(128, device=dev) * 0.1 + 2.0 ** -18)
+    for _ in range(reps):
+        F.gdn_dense(x, beta, gm, False)
 torch.cuda.synchronize()
 print("ok")
