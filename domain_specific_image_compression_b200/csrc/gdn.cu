@@ -28,8 +28,14 @@ __device__ __forceinline__ void eff_params(const float *__restrict__ beta_param,
     gamma = __fadd_rn(__fmul_rn(w, w), -kOffset);  // layers.py:21
 }
 
+// optional fused conv bias: PyTorch runs conv (no bias) -> add_(bias) -> GDN as three passes; the add is folded in here
+// (rn(x + b), the same rounding) and its gradient (sum of dx per channel) comes out of the backward's reduction for free.
+// -0.0f is the neutral element that keeps every bit of x, including the sign of zero.
+__device__ __forceinline__ float load_bias(const float *__restrict__ bias, int c) { return bias != nullptr ? __ldg(bias + c) : -0.0f; }
+
 template <bool INVERSE>
-__device__ __forceinline__ float gdn1(float x, float beta, float gamma) {
+__device__ __forceinline__ float gdn1(float xin, float bias, float beta, float gamma) {
+    float x = __fadd_rn(xin, bias);
     float x2 = __fmul_rn(x, x);
     float p = __fmul_rn(gamma, x2);
     float s = __fadd_rn(beta, p);
@@ -41,13 +47,15 @@ __device__ __forceinline__ float gdn1(float x, float beta, float gamma) {
 // per-vector integer work is one add (the first version divided every vector index by HW/4 and C: 15 of its 30
 // instructions per element were index math, ncu r01).
 template <bool INVERSE>
-__global__ void __launch_bounds__(kThreads) gdn_fwd_vec_kernel(const float4 *__restrict__ x, const float *__restrict__ beta_param,
+__global__ void __launch_bounds__(kThreads) gdn_fwd_vec_kernel(const float4 *__restrict__ x, const float *__restrict__ bias_p,
+                                                               const float *__restrict__ beta_param,
                                                                const float *__restrict__ gamma_weight, int C, int hw4, int chunks,
                                                                float4 *__restrict__ y) {
     const int plane = blockIdx.x / chunks;
     const int chunk = blockIdx.x - plane * chunks;
     float beta, gamma;
     eff_params(beta_param, gamma_weight, plane % C, beta, gamma);
+    const float bias = load_bias(bias_p, plane % C);
     const int v_begin = chunk * kChunk4, v_end = min(v_begin + kChunk4, hw4);
     const float4 *xp = x + (long)plane * hw4;
     float4 *yp = y + (long)plane * hw4;
@@ -63,10 +71,10 @@ __global__ void __launch_bounds__(kThreads) gdn_fwd_vec_kernel(const float4 *__r
             int v = v0 + k * kThreads;
             if (v < v_end) {
                 float4 o;
-                o.x = gdn1<INVERSE>(a[k].x, beta, gamma);
-                o.y = gdn1<INVERSE>(a[k].y, beta, gamma);
-                o.z = gdn1<INVERSE>(a[k].z, beta, gamma);
-                o.w = gdn1<INVERSE>(a[k].w, beta, gamma);
+                o.x = gdn1<INVERSE>(a[k].x, bias, beta, gamma);
+                o.y = gdn1<INVERSE>(a[k].y, bias, beta, gamma);
+                o.z = gdn1<INVERSE>(a[k].z, bias, beta, gamma);
+                o.w = gdn1<INVERSE>(a[k].w, bias, beta, gamma);
                 stg_stream(yp + v, o);
             }
         }
@@ -74,14 +82,15 @@ __global__ void __launch_bounds__(kThreads) gdn_fwd_vec_kernel(const float4 *__r
 }
 
 template <bool INVERSE>
-__global__ void __launch_bounds__(kThreads) gdn_fwd_scalar_kernel(const float *__restrict__ x, const float *__restrict__ beta_param,
+__global__ void __launch_bounds__(kThreads) gdn_fwd_scalar_kernel(const float *__restrict__ x, const float *__restrict__ bias_p,
+                                                                  const float *__restrict__ beta_param,
                                                                   const float *__restrict__ gamma_weight, long n, int HW, int C,
                                                                   int channels_last, float *__restrict__ y) {
     for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long)gridDim.x * kThreads) {
         int c = channels_last ? (int)(i % C) : (int)((i / HW) % C);
         float beta, gamma;
         eff_params(beta_param, gamma_weight, c, beta, gamma);
-        y[i] = gdn1<INVERSE>(x[i], beta, gamma);
+        y[i] = gdn1<INVERSE>(x[i], load_bias(bias_p, c), beta, gamma);
     }
 }
 
@@ -89,20 +98,25 @@ __global__ void __launch_bounds__(kThreads) gdn_fwd_scalar_kernel(const float *_
 // of C/4 and every stride is a multiple of blockDim, so a thread keeps ONE channel quad for its whole life: the
 // re-parameterised beta/gamma are hoisted into registers and (backward) the per-channel sums need no atomics.
 struct Quad {
-    float b[4], g[4];
+    float b[4], g[4], a[4];  // beta, gamma, conv bias
 };
-__device__ __forceinline__ Quad load_quad(const float *__restrict__ beta_param, const float *__restrict__ gamma_weight, int c) {
+__device__ __forceinline__ Quad load_quad(const float *__restrict__ bias_p, const float *__restrict__ beta_param,
+                                          const float *__restrict__ gamma_weight, int c) {
     Quad q;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) eff_params(beta_param, gamma_weight, c + j, q.b[j], q.g[j]);
+    for (int j = 0; j < 4; ++j) {
+        eff_params(beta_param, gamma_weight, c + j, q.b[j], q.g[j]);
+        q.a[j] = load_bias(bias_p, c + j);
+    }
     return q;
 }
 
 template <bool INVERSE>
-__global__ void __launch_bounds__(kThreads) gdn_fwd_nhwc_kernel(const float4 *__restrict__ x, const float *__restrict__ beta_param,
+__global__ void __launch_bounds__(kThreads) gdn_fwd_nhwc_kernel(const float4 *__restrict__ x, const float *__restrict__ bias_p,
+                                                                const float *__restrict__ beta_param,
                                                                 const float *__restrict__ gamma_weight, unsigned n4, int c4,
                                                                 float4 *__restrict__ y) {
-    const Quad q = load_quad(beta_param, gamma_weight, (int)(threadIdx.x % c4) * 4);
+    const Quad q = load_quad(bias_p, beta_param, gamma_weight, (int)(threadIdx.x % c4) * 4);
     const unsigned stride = gridDim.x * blockDim.x * kUnroll;
     for (unsigned v0 = blockIdx.x * (blockDim.x * kUnroll) + threadIdx.x; v0 < n4; v0 += stride) {
         float4 a[kUnroll];
@@ -116,10 +130,10 @@ __global__ void __launch_bounds__(kThreads) gdn_fwd_nhwc_kernel(const float4 *__
             unsigned v = v0 + k * blockDim.x;
             if (v < n4) {
                 float4 o;
-                o.x = gdn1<INVERSE>(a[k].x, q.b[0], q.g[0]);
-                o.y = gdn1<INVERSE>(a[k].y, q.b[1], q.g[1]);
-                o.z = gdn1<INVERSE>(a[k].z, q.b[2], q.g[2]);
-                o.w = gdn1<INVERSE>(a[k].w, q.b[3], q.g[3]);
+                o.x = gdn1<INVERSE>(a[k].x, q.a[0], q.b[0], q.g[0]);
+                o.y = gdn1<INVERSE>(a[k].y, q.a[1], q.b[1], q.g[1]);
+                o.z = gdn1<INVERSE>(a[k].z, q.a[2], q.b[2], q.g[2]);
+                o.w = gdn1<INVERSE>(a[k].w, q.a[3], q.b[3], q.g[3]);
                 stg_stream(y + v, o);
             }
         }
@@ -146,32 +160,38 @@ __device__ __forceinline__ void gdn_bwd1(float x, float g, float beta, float gam
     hg = hb * x2;
 }
 
-__device__ __forceinline__ void block_sum2(float &a, float &b) {
-    __shared__ float sa[kThreads / 32], sb[kThreads / 32];
+__device__ __forceinline__ void block_sum3(float &a, float &b, float &c) {
+    __shared__ float sa[kThreads / 32], sb[kThreads / 32], sc[kThreads / 32];
     a = warp_sum(a);
     b = warp_sum(b);
+    c = warp_sum(c);
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { sa[warp] = a; sb[warp] = b; }
+    if (lane == 0) { sa[warp] = a; sb[warp] = b; sc[warp] = c; }
     __syncthreads();
     if (warp == 0) {
         a = lane < kThreads / 32 ? sa[lane] : 0.f;
         b = lane < kThreads / 32 ? sb[lane] : 0.f;
+        c = lane < kThreads / 32 ? sc[lane] : 0.f;
         a = warp_sum(a);
         b = warp_sum(b);
+        c = warp_sum(c);
     }
 }
 
-// one CTA = one (plane, chunk) unit; partials laid out [C][B*chunks] so the finalize kernel reads them contiguously
+// one CTA = one (plane, chunk) unit; partials laid out [3][C][B*chunks] (dbeta, dgamma, dbias) so the finalize kernel
+// reads them contiguously
 template <bool INVERSE, bool VEC>
-__global__ void __launch_bounds__(kThreads) gdn_bwd_kernel(const float *__restrict__ x, const float *__restrict__ g,
-                                                           const float *__restrict__ beta_param, const float *__restrict__ gamma_weight,
-                                                           int C, int HW, int chunks, float *__restrict__ dx, float *__restrict__ part) {
+__global__ void __launch_bounds__(kThreads) gdn_bwd_kernel(const float *__restrict__ x, const float *__restrict__ bias_p,
+                                                           const float *__restrict__ g, const float *__restrict__ beta_param,
+                                                           const float *__restrict__ gamma_weight, int C, int HW, int chunks,
+                                                           float *__restrict__ dx, float *__restrict__ part) {
     const int plane = blockIdx.x / chunks;
     const int chunk = blockIdx.x - plane * chunks;
     const int c = plane % C, b = plane / C;
     float beta, gamma;
     eff_params(beta_param, gamma_weight, c, beta, gamma);
-    float acc_b = 0.f, acc_g = 0.f;
+    const float bias = load_bias(bias_p, c);
+    float acc_b = 0.f, acc_g = 0.f, acc_x = 0.f;
     const long base = (long)plane * HW;
     if (VEC) {
         const int hw4 = HW >> 2;
@@ -192,10 +212,11 @@ __global__ void __launch_bounds__(kThreads) gdn_bwd_kernel(const float *__restri
                 if (v < v_end) {
                     float4 o;
                     float hb, hg;
-                    gdn_bwd1<INVERSE>(xa[k].x, ga[k].x, beta, gamma, o.x, hb, hg); acc_b += hb; acc_g += hg;
-                    gdn_bwd1<INVERSE>(xa[k].y, ga[k].y, beta, gamma, o.y, hb, hg); acc_b += hb; acc_g += hg;
-                    gdn_bwd1<INVERSE>(xa[k].z, ga[k].z, beta, gamma, o.z, hb, hg); acc_b += hb; acc_g += hg;
-                    gdn_bwd1<INVERSE>(xa[k].w, ga[k].w, beta, gamma, o.w, hb, hg); acc_b += hb; acc_g += hg;
+                    gdn_bwd1<INVERSE>(xa[k].x + bias, ga[k].x, beta, gamma, o.x, hb, hg); acc_b += hb; acc_g += hg;
+                    gdn_bwd1<INVERSE>(xa[k].y + bias, ga[k].y, beta, gamma, o.y, hb, hg); acc_b += hb; acc_g += hg;
+                    gdn_bwd1<INVERSE>(xa[k].z + bias, ga[k].z, beta, gamma, o.z, hb, hg); acc_b += hb; acc_g += hg;
+                    gdn_bwd1<INVERSE>(xa[k].w + bias, ga[k].w, beta, gamma, o.w, hb, hg); acc_b += hb; acc_g += hg;
+                    acc_x += (o.x + o.y) + (o.z + o.w);
                     stg_stream(dx4 + v, o);
                 }
             }
@@ -204,32 +225,34 @@ __global__ void __launch_bounds__(kThreads) gdn_bwd_kernel(const float *__restri
         const int e_begin = chunk * kChunk4 * 4, e_end = min(e_begin + kChunk4 * 4, HW);
         for (int e = e_begin + threadIdx.x; e < e_end; e += kThreads) {
             float o, hb, hg;
-            gdn_bwd1<INVERSE>(x[base + e], g[base + e], beta, gamma, o, hb, hg);
+            gdn_bwd1<INVERSE>(x[base + e] + bias, g[base + e], beta, gamma, o, hb, hg);
             dx[base + e] = o;
             acc_b += hb;
             acc_g += hg;
+            acc_x += o;
         }
     }
-    block_sum2(acc_b, acc_g);
+    block_sum3(acc_b, acc_g, acc_x);
     if (threadIdx.x == 0) {
         const long P = (long)gridDim.x / C;  // = B * chunks partials per channel
         long slot = (long)c * P + (long)b * chunks + chunk;
         part[slot] = acc_b;
         part[(long)C * P + slot] = acc_g;
+        part[2 * (long)C * P + slot] = acc_x;
     }
 }
 
-// NHWC backward: persistent CTAs, thread-private sums for its channel quad, one smem fold per CTA, partials [C][gridDim.x]
+// NHWC backward: persistent CTAs, thread-private sums for its channel quad, one smem fold per CTA, partials [3][C][gridDim.x]
 template <bool INVERSE>
-__global__ void __launch_bounds__(kThreads) gdn_bwd_nhwc_kernel(const float4 *__restrict__ x, const float4 *__restrict__ g,
-                                                                const float *__restrict__ beta_param,
+__global__ void __launch_bounds__(kThreads) gdn_bwd_nhwc_kernel(const float4 *__restrict__ x, const float *__restrict__ bias_p,
+                                                                const float4 *__restrict__ g, const float *__restrict__ beta_param,
                                                                 const float *__restrict__ gamma_weight, unsigned n4, int C,
                                                                 float4 *__restrict__ dx, float *__restrict__ part) {
-    extern __shared__ float sm[];  // [blockDim.x][8]
+    extern __shared__ float sm[];  // [blockDim.x][12]
     const int c4 = C >> 2;
     const int cq = (int)(threadIdx.x % c4);
-    const Quad q = load_quad(beta_param, gamma_weight, cq * 4);
-    float ab[4] = {0.f, 0.f, 0.f, 0.f}, ag[4] = {0.f, 0.f, 0.f, 0.f};
+    const Quad q = load_quad(bias_p, beta_param, gamma_weight, cq * 4);
+    float ab[4] = {0.f, 0.f, 0.f, 0.f}, ag[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
     constexpr int U = 2;
     const unsigned stride = gridDim.x * blockDim.x * U;
     for (unsigned v0 = blockIdx.x * (blockDim.x * U) + threadIdx.x; v0 < n4; v0 += stride) {
@@ -245,23 +268,23 @@ __global__ void __launch_bounds__(kThreads) gdn_bwd_nhwc_kernel(const float4 *__
             if (v < n4) {
                 float4 o;
                 float hb, hg;
-                gdn_bwd1<INVERSE>(xa[k].x, ga[k].x, q.b[0], q.g[0], o.x, hb, hg); ab[0] += hb; ag[0] += hg;
-                gdn_bwd1<INVERSE>(xa[k].y, ga[k].y, q.b[1], q.g[1], o.y, hb, hg); ab[1] += hb; ag[1] += hg;
-                gdn_bwd1<INVERSE>(xa[k].z, ga[k].z, q.b[2], q.g[2], o.z, hb, hg); ab[2] += hb; ag[2] += hg;
-                gdn_bwd1<INVERSE>(xa[k].w, ga[k].w, q.b[3], q.g[3], o.w, hb, hg); ab[3] += hb; ag[3] += hg;
+                gdn_bwd1<INVERSE>(xa[k].x + q.a[0], ga[k].x, q.b[0], q.g[0], o.x, hb, hg); ab[0] += hb; ag[0] += hg; ax[0] += o.x;
+                gdn_bwd1<INVERSE>(xa[k].y + q.a[1], ga[k].y, q.b[1], q.g[1], o.y, hb, hg); ab[1] += hb; ag[1] += hg; ax[1] += o.y;
+                gdn_bwd1<INVERSE>(xa[k].z + q.a[2], ga[k].z, q.b[2], q.g[2], o.z, hb, hg); ab[2] += hb; ag[2] += hg; ax[2] += o.z;
+                gdn_bwd1<INVERSE>(xa[k].w + q.a[3], ga[k].w, q.b[3], q.g[3], o.w, hb, hg); ab[3] += hb; ag[3] += hg; ax[3] += o.w;
                 stg_stream(dx + v, o);
             }
         }
     }
-    float *mine = sm + threadIdx.x * 8;
+    float *mine = sm + threadIdx.x * 12;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { mine[j] = ab[j]; mine[4 + j] = ag[j]; }
+    for (int j = 0; j < 4; ++j) { mine[j] = ab[j]; mine[4 + j] = ag[j]; mine[8 + j] = ax[j]; }
     __syncthreads();
     if ((int)threadIdx.x < c4) {  // fold the blockDim/c4 threads that share this quad, fixed order
-        float sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f};
+        float sb[4] = {0.f, 0.f, 0.f, 0.f}, sg[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f};
         for (unsigned t = threadIdx.x; t < blockDim.x; t += c4) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { sb[j] += sm[t * 8 + j]; sg[j] += sm[t * 8 + 4 + j]; }
+            for (int j = 0; j < 4; ++j) { sb[j] += sm[t * 12 + j]; sg[j] += sm[t * 12 + 4 + j]; sx[j] += sm[t * 12 + 8 + j]; }
         }
         const long P = gridDim.x;
 #pragma unroll
@@ -269,6 +292,7 @@ __global__ void __launch_bounds__(kThreads) gdn_bwd_nhwc_kernel(const float4 *__
             long c = cq * 4 + j;
             part[c * P + blockIdx.x] = sb[j];
             part[(long)C * P + c * P + blockIdx.x] = sg[j];
+            part[2 * (long)C * P + c * P + blockIdx.x] = sx[j];
         }
     }
 }
@@ -276,23 +300,28 @@ __global__ void __launch_bounds__(kThreads) gdn_bwd_nhwc_kernel(const float4 *__
 // one CTA per channel: fixed-order float64 fold + chain rule through the squared re-parameterisation (layers.py:20-21)
 __global__ void __launch_bounds__(128) gdn_bwd_finalize_kernel(const float *__restrict__ part, const float *__restrict__ beta_param,
                                                                const float *__restrict__ gamma_weight, int C, long P,
-                                                               float *__restrict__ dbeta_param, float *__restrict__ dgamma_weight) {
+                                                               float *__restrict__ dbeta_param, float *__restrict__ dgamma_weight,
+                                                               float *__restrict__ dbias) {
     const int c = blockIdx.x;
-    double sb = 0.0, sg = 0.0;
+    double sb = 0.0, sg = 0.0, sx = 0.0;
     for (long i = threadIdx.x; i < P; i += 128) {
         sb += (double)part[(long)c * P + i];
         sg += (double)part[(long)C * P + (long)c * P + i];
+        sx += (double)part[2 * (long)C * P + (long)c * P + i];
     }
-    __shared__ double shb[4], shg[4];
+    __shared__ double shb[4], shg[4], shx[4];
     sb = warp_sum(sb);
     sg = warp_sum(sg);
-    if ((threadIdx.x & 31) == 0) { shb[threadIdx.x >> 5] = sb; shg[threadIdx.x >> 5] = sg; }
+    sx = warp_sum(sx);
+    if ((threadIdx.x & 31) == 0) { shb[threadIdx.x >> 5] = sb; shg[threadIdx.x >> 5] = sg; shx[threadIdx.x >> 5] = sx; }
     __syncthreads();
     if (threadIdx.x == 0) {
         sb = (shb[0] + shb[1]) + (shb[2] + shb[3]);
         sg = (shg[0] + shg[1]) + (shg[2] + shg[3]);
+        sx = (shx[0] + shx[1]) + (shx[2] + shx[3]);
         if (dbeta_param) dbeta_param[c] = (float)(sb * 2.0 * (double)beta_param[c]);
         if (dgamma_weight) dgamma_weight[c] = (float)(sg * 2.0 * (double)gamma_weight[c]);
+        if (dbias) dbias[c] = (float)sx;
     }
 }
 
@@ -309,8 +338,8 @@ inline int bwd_chunks(int HW) {
 
 using namespace sic;
 
-extern "C" int sic_gdn_fwd(const float *x, const float *beta_param, const float *gamma_weight, int B, int C, int HW, int inverse,
-                           int channels_last, float *y, void *stream) {
+extern "C" int sic_gdn_fwd(const float *x, const float *bias, const float *beta_param, const float *gamma_weight, int B, int C,
+                           int HW, int inverse, int channels_last, float *y, void *stream) {
     SIC_CHECK_ARG(B > 0 && C > 0 && HW > 0, "sic_gdn_fwd: empty shape B=%d C=%d HW=%d", B, C, HW);
     SIC_CHECK_ARG(x && y && beta_param && gamma_weight, "sic_gdn_fwd: null pointer");
     const long n = (long)B * C * HW;
@@ -321,20 +350,20 @@ extern "C" int sic_gdn_fwd(const float *x, const float *beta_param, const float 
         const int hw4 = HW / 4, chunks = (hw4 + kChunk4 - 1) / kChunk4;
         const long units = (long)B * C * chunks;
         SIC_CHECK_ARG(units < (1L << 31), "sic_gdn_fwd: too many units");
-        if (inverse) gdn_fwd_vec_kernel<true><<<(unsigned)units, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, C, hw4, chunks, (float4 *)y);
-        else gdn_fwd_vec_kernel<false><<<(unsigned)units, kThreads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, C, hw4, chunks, (float4 *)y);
+        if (inverse) gdn_fwd_vec_kernel<true><<<(unsigned)units, kThreads, 0, st>>>((const float4 *)x, bias, beta_param, gamma_weight, C, hw4, chunks, (float4 *)y);
+        else gdn_fwd_vec_kernel<false><<<(unsigned)units, kThreads, 0, st>>>((const float4 *)x, bias, beta_param, gamma_weight, C, hw4, chunks, (float4 *)y);
     } else if (channels_last && C % 4 == 0 && C <= 4 * kThreads && al) {
         unsigned n4 = (unsigned)(n / 4);
         const int c4 = C / 4, threads = nhwc_threads(C);
         long want = ((long)n4 + threads * kUnroll - 1) / (threads * kUnroll);
         unsigned grid = (unsigned)(want < (long)sms * 8 ? want : (long)sms * 8);
-        if (inverse) gdn_fwd_nhwc_kernel<true><<<grid, threads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, c4, (float4 *)y);
-        else gdn_fwd_nhwc_kernel<false><<<grid, threads, 0, st>>>((const float4 *)x, beta_param, gamma_weight, n4, c4, (float4 *)y);
+        if (inverse) gdn_fwd_nhwc_kernel<true><<<grid, threads, 0, st>>>((const float4 *)x, bias, beta_param, gamma_weight, n4, c4, (float4 *)y);
+        else gdn_fwd_nhwc_kernel<false><<<grid, threads, 0, st>>>((const float4 *)x, bias, beta_param, gamma_weight, n4, c4, (float4 *)y);
     } else {
         long want = (n + kThreads - 1) / kThreads;
         unsigned grid = (unsigned)(want < (long)sms * 16 ? want : (long)sms * 16);
-        if (inverse) gdn_fwd_scalar_kernel<true><<<grid, kThreads, 0, st>>>(x, beta_param, gamma_weight, n, HW, C, channels_last, y);
-        else gdn_fwd_scalar_kernel<false><<<grid, kThreads, 0, st>>>(x, beta_param, gamma_weight, n, HW, C, channels_last, y);
+        if (inverse) gdn_fwd_scalar_kernel<true><<<grid, kThreads, 0, st>>>(x, bias, beta_param, gamma_weight, n, HW, C, channels_last, y);
+        else gdn_fwd_scalar_kernel<false><<<grid, kThreads, 0, st>>>(x, bias, beta_param, gamma_weight, n, HW, C, channels_last, y);
     }
     SIC_CHECK_LAUNCH("sic_gdn_fwd");
     return 0;
@@ -342,14 +371,14 @@ extern "C" int sic_gdn_fwd(const float *x, const float *beta_param, const float 
 
 extern "C" size_t sic_gdn_bwd_workspace_bytes(int B, int C, int HW) {
     if (B <= 0 || C <= 0 || HW <= 0) return 0;
-    size_t nchw = (size_t)2 * C * B * bwd_chunks(HW) * sizeof(float);
-    size_t nhwc = (size_t)2 * C * nhwc_bwd_grid() * sizeof(float);
+    size_t nchw = (size_t)3 * C * B * bwd_chunks(HW) * sizeof(float);
+    size_t nhwc = (size_t)3 * C * nhwc_bwd_grid() * sizeof(float);
     return nchw > nhwc ? nchw : nhwc;
 }
 
-extern "C" int sic_gdn_bwd(const float *x, const float *g, const float *beta_param, const float *gamma_weight, int B, int C,
-                           int HW, int inverse, int channels_last, float *dx, float *dbeta_param, float *dgamma_weight,
-                           void *workspace, size_t workspace_bytes, void *stream) {
+extern "C" int sic_gdn_bwd(const float *x, const float *bias, const float *g, const float *beta_param, const float *gamma_weight,
+                           int B, int C, int HW, int inverse, int channels_last, float *dx, float *dbias, float *dbeta_param,
+                           float *dgamma_weight, void *workspace, size_t workspace_bytes, void *stream) {
     SIC_CHECK_ARG(B > 0 && C > 0 && HW > 0, "sic_gdn_bwd: empty shape B=%d C=%d HW=%d", B, C, HW);
     SIC_CHECK_ARG(x && g && dx && beta_param && gamma_weight && workspace, "sic_gdn_bwd: null pointer");
     if (workspace_bytes < sic_gdn_bwd_workspace_bytes(B, C, HW)) {
@@ -368,11 +397,11 @@ extern "C" int sic_gdn_bwd(const float *x, const float *g, const float *beta_par
         const unsigned n4 = (unsigned)(n / 4);
         long want = ((long)n4 + threads * 2 - 1) / (threads * 2);
         const unsigned grid = (unsigned)(want < nhwc_bwd_grid() ? want : nhwc_bwd_grid());
-        const size_t smem = (size_t)threads * 8 * sizeof(float);
-        if (inverse) gdn_bwd_nhwc_kernel<true><<<grid, threads, smem, st>>>((const float4 *)x, (const float4 *)g, beta_param, gamma_weight, n4, C, (float4 *)dx, part);
-        else gdn_bwd_nhwc_kernel<false><<<grid, threads, smem, st>>>((const float4 *)x, (const float4 *)g, beta_param, gamma_weight, n4, C, (float4 *)dx, part);
+        const size_t smem = (size_t)threads * 12 * sizeof(float);
+        if (inverse) gdn_bwd_nhwc_kernel<true><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, (float4 *)dx, part);
+        else gdn_bwd_nhwc_kernel<false><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, (float4 *)dx, part);
         SIC_CHECK_LAUNCH("sic_gdn_bwd (nhwc)");
-        gdn_bwd_finalize_kernel<<<C, 128, 0, st>>>(part, beta_param, gamma_weight, C, (long)grid, dbeta_param, dgamma_weight);
+        gdn_bwd_finalize_kernel<<<C, 128, 0, st>>>(part, beta_param, gamma_weight, C, (long)grid, dbeta_param, dgamma_weight, dbias);
         SIC_CHECK_LAUNCH("sic_gdn_bwd finalize");
         return 0;
     }
@@ -381,14 +410,14 @@ extern "C" int sic_gdn_bwd(const float *x, const float *g, const float *beta_par
     SIC_CHECK_ARG(units < (1L << 31), "sic_gdn_bwd: too many units");
     const bool vec = HW % 4 == 0 && aligned16(x) && aligned16(g) && aligned16(dx);
     if (inverse) {
-        if (vec) gdn_bwd_kernel<true, true><<<(unsigned)units, kThreads, 0, st>>>(x, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
-        else gdn_bwd_kernel<true, false><<<(unsigned)units, kThreads, 0, st>>>(x, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
+        if (vec) gdn_bwd_kernel<true, true><<<(unsigned)units, kThreads, 0, st>>>(x, bias, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
+        else gdn_bwd_kernel<true, false><<<(unsigned)units, kThreads, 0, st>>>(x, bias, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
     } else {
-        if (vec) gdn_bwd_kernel<false, true><<<(unsigned)units, kThreads, 0, st>>>(x, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
-        else gdn_bwd_kernel<false, false><<<(unsigned)units, kThreads, 0, st>>>(x, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
+        if (vec) gdn_bwd_kernel<false, true><<<(unsigned)units, kThreads, 0, st>>>(x, bias, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
+        else gdn_bwd_kernel<false, false><<<(unsigned)units, kThreads, 0, st>>>(x, bias, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
     }
     SIC_CHECK_LAUNCH("sic_gdn_bwd");
-    gdn_bwd_finalize_kernel<<<C, 128, 0, st>>>(part, beta_param, gamma_weight, C, (long)B * chunks, dbeta_param, dgamma_weight);
+    gdn_bwd_finalize_kernel<<<C, 128, 0, st>>>(part, beta_param, gamma_weight, C, (long)B * chunks, dbeta_param, dgamma_weight, dbias);
     SIC_CHECK_LAUNCH("sic_gdn_bwd finalize");
     return 0;
 }

@@ -172,9 +172,10 @@ def bottleneck(y: torch.Tensor, sigma: torch.Tensor, nu: Optional[torch.Tensor] 
 # K2
 class _GDN(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, beta_param, gamma_weight, inverse: bool):
+    def forward(ctx, x, beta_param, gamma_weight, inverse: bool, bias=None):
         lib = _lib.load()
         x, cl = _dense_layout(x, "x")
+        bias = None if bias is None else _require_cuda_f32(bias, "bias")
         back_to_cl = False
         if cl and x.shape[1] % 4 != 0:                # NHWC kernels walk channel quads; odd channel counts go through NCHW
             x, cl, back_to_cl = x.contiguous(), 0, True
@@ -187,16 +188,18 @@ class _GDN(torch.autograd.Function):
         HW = x.numel() // (B * C)
         y = torch.empty_like(x)                       # keeps x's memory format (NCHW or channels_last)
         with torch.cuda.device(x.device):
-            _launch(lib.sic_gdn_fwd(_ptr(x), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, int(inverse), cl, _ptr(y), _stream()),
-                    "sic_gdn_fwd")
-        ctx.save_for_backward(x, beta_param, gamma_weight)
+            _launch(lib.sic_gdn_fwd(_ptr(x), _ptr(bias), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, int(inverse), cl, _ptr(y),
+                                    _stream()), "sic_gdn_fwd")
+        if bias is not None and bias.numel() != C:
+            raise _lib.SicError(f"bias has {bias.numel()} entries for {C} channels")
+        ctx.save_for_backward(x, beta_param, gamma_weight, bias)
         ctx.cfg = (B, C, HW, int(inverse), cl)
         return y.contiguous(memory_format=torch.channels_last) if back_to_cl else y
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
-        x, beta_param, gamma_weight = ctx.saved_tensors
+        x, beta_param, gamma_weight, bias = ctx.saved_tensors
         B, C, HW, inverse, cl = ctx.cfg
         if cl:                                        # the gradient must be walked in x's memory order
             g = _dense_layout(g.contiguous(memory_format=torch.channels_last), "grad_output")[0]
@@ -205,19 +208,23 @@ class _GDN(torch.autograd.Function):
         dx = torch.empty_like(x)
         dbeta = torch.empty_like(beta_param)
         dgamma = torch.empty_like(gamma_weight)
+        dbias = torch.empty_like(bias) if bias is not None else None
         nws = lib.sic_gdn_bwd_workspace_bytes(B, C, HW)
         ws = _workspace(x.device, nws, "scratch")
         with torch.cuda.device(x.device):
-            _lib.check(lib.sic_gdn_bwd(_ptr(x), _ptr(g), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, inverse, cl, _ptr(dx),
-                                       _ptr(dbeta), _ptr(dgamma), _ptr(ws), ws.numel(), _stream()), "sic_gdn_bwd")
+            _lib.check(lib.sic_gdn_bwd(_ptr(x), _ptr(bias), _ptr(g), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, inverse, cl,
+                                       _ptr(dx), _ptr(dbias), _ptr(dbeta), _ptr(dgamma), _ptr(ws), ws.numel(), _stream()),
+                       "sic_gdn_bwd")
         global launch_count
         launch_count += 2
-        return dx, dbeta, dgamma.view(ctx.w_shape), None
+        return dx, dbeta, dgamma.view(ctx.w_shape), None, dbias
 
 
-def gdn(x: torch.Tensor, beta_param: torch.Tensor, gamma_weight: torch.Tensor, inverse: bool = False) -> torch.Tensor:
-    """Diagonal GDN/IGDN (K2), bit-exact with layers.py:19-27 on the same device arithmetic."""
-    return _GDN.apply(x, beta_param, gamma_weight, inverse)
+def gdn(x: torch.Tensor, beta_param: torch.Tensor, gamma_weight: torch.Tensor, inverse: bool = False,
+        bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Diagonal GDN/IGDN (K2), bit-exact with layers.py:19-27 on the same device arithmetic.  `bias`: the producing
+    convolution's bias, folded in as GDN(x + bias) (same rounding as PyTorch's conv -> add_(bias) -> GDN)."""
+    return _GDN.apply(x, beta_param, gamma_weight, inverse, bias)
 
 
 class _GDNDense(torch.autograd.Function):

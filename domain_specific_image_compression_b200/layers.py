@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import functional as F_sic
 
@@ -33,6 +34,32 @@ class GDN(nn.Module):
         if self.dense:
             return F_sic.gdn_dense(x, self.beta, self.gamma, self.inverse)
         return F_sic.gdn(x, self.beta, self.gamma_conv.weight, self.inverse)
+
+
+FUSE_CONV_BIAS = True      # fold each convolution's bias add (and its gradient reduction) into the following GDN kernel
+
+
+def _run(seq: nn.Sequential, x):
+    """nn.Sequential forward with one fusion: conv / conv-transpose followed by a diagonal GDN runs as conv WITHOUT bias,
+    then GDN(x + bias) in the CUDA kernel.  PyTorch's own path is conv (cuDNN, no bias) -> add_(bias) -> ..., so the values
+    are bit-identical; what disappears is one full read+write pass per site and the per-site bias-gradient reduction."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        nxt = mods[i + 1] if i + 1 < len(mods) else None
+        if (FUSE_CONV_BIAS and isinstance(nxt, GDN) and not nxt.dense and m.__class__ in (nn.Conv2d, nn.ConvTranspose2d)
+                and m.bias is not None and x.is_cuda):
+            if isinstance(m, nn.Conv2d):
+                t = F.conv2d(x, m.weight, None, m.stride, m.padding, m.dilation, m.groups)
+            else:
+                t = F.conv_transpose2d(x, m.weight, None, m.stride, m.padding, m.output_padding, m.groups, m.dilation)
+            x = F_sic.gdn(t, nxt.beta, nxt.gamma_conv.weight, nxt.inverse, bias=m.bias)
+            i += 2
+        else:
+            x = m(x)
+            i += 1
+    return x
 
 
 def _conv(cin, cout, k, stride=1):
@@ -73,7 +100,7 @@ class AnalysisTransform(nn.Module):
         self.g_a = _stack(spec)
 
     def forward(self, x):
-        return self.g_a(x)
+        return _run(self.g_a, x)
 
 
 class SynthesisTransform(nn.Module):
@@ -88,7 +115,7 @@ class SynthesisTransform(nn.Module):
         self.g_s = _stack(spec)
 
     def forward(self, y_hat):
-        return self.g_s(y_hat)
+        return _run(self.g_s, y_hat)
 
 
 class HyperAnalysis(nn.Module):

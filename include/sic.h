@@ -84,13 +84,16 @@ int sic_bottleneck_bwd(const float *y_tilde, const float *mu, const float *sigma
  *   beta_param [C], gamma_weight [C] are the STORED parameters (`beta`, `gamma_conv.weight`); the re-parameterisation
  *   beta = beta_param^2 - 2^-18, gamma = w^2 - 2^-18 (layers.py:20-21) is applied inside.
  *   Forward replays the eager rounding sequence with IEEE ops (mul, mul, add, sqrt.rn, div.rn | mul): bit-exact.
- *   channels_last != 0: x is stored NHWC (channel index = i % C) instead of NCHW. */
-int sic_gdn_fwd(const float *x, const float *beta_param, const float *gamma_weight, int B, int C, int HW, int inverse,
-                int channels_last, float *y, void *stream);
+ *   channels_last != 0: x is stored NHWC (channel index = i % C) instead of NCHW.
+ *   bias (nullable): the per-channel bias of the producing convolution, folded in as y = GDN(x + bias) with the same
+ *   rounding as PyTorch's separate add_ (conv -> add_(bias) -> GDN, layers.py:29-31,49-73); backward then also returns
+ *   dbias[c] = sum dx, which saves the add pass and the bias-gradient reduction over every GDN site. */
+int sic_gdn_fwd(const float *x, const float *bias, const float *beta_param, const float *gamma_weight, int B, int C, int HW,
+                int inverse, int channels_last, float *y, void *stream);
 size_t sic_gdn_bwd_workspace_bytes(int B, int C, int HW);
-int sic_gdn_bwd(const float *x, const float *g, const float *beta_param, const float *gamma_weight, int B, int C, int HW,
-                int inverse, int channels_last, float *dx, float *dbeta_param, float *dgamma_weight, void *workspace,
-                size_t workspace_bytes, void *stream);
+int sic_gdn_bwd(const float *x, const float *bias, const float *g, const float *beta_param, const float *gamma_weight, int B,
+                int C, int HW, int inverse, int channels_last, float *dx, float *dbias, float *dbeta_param,
+                float *dgamma_weight, void *workspace, size_t workspace_bytes, void *stream);
 
 /* G3  GDN / IGDN with a DENSE C x C gamma (north_star's tensor-core contraction; the reference stores the matrix,
  * layers.py:13, but never uses it: SURVEY.md D3).  s[p,i] = beta_i + sum_j gamma_ij x[p,j]^2, y = x/sqrt(s) | x*sqrt(s).

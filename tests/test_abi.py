@@ -39,7 +39,7 @@ def test_argument_errors_are_reported_not_thrown():
     lib = _lib.load()
     rc = lib.sic_bottleneck_fwd(None, None, None, None, None, None, 0, 1, 1, 0, 0, 0, None, None, None, None, 0, None)
     assert rc == -1 and b"empty shape" in lib.sic_last_error()
-    rc = lib.sic_gdn_fwd(None, None, None, 1, 1, 1, 0, 0, None, None)
+    rc = lib.sic_gdn_fwd(None, None, None, None, 1, 1, 1, 0, 0, None, None)
     assert rc == -1 and b"null" in lib.sic_last_error()
     rc = lib.sic_build_cdf_tables(7, None, None, 1, 1, 1, None, None, 4, None, None)
     assert rc == -1

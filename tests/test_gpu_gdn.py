@@ -217,3 +217,32 @@ def test_dense_gdn_backward_and_module():
     with pytest.raises(sic.SicError):
         F = _F()
         F.gdn_dense(torch.randn(1, 192, 4, 4, device="cuda"), torch.ones(192, device="cuda"), torch.ones(192, 192, device="cuda"))
+
+
+@pytest.mark.parametrize("fmt", [torch.contiguous_format, torch.channels_last])
+@pytest.mark.parametrize("inverse", [False, True])
+def test_fused_conv_bias_is_bit_exact_and_returns_bias_gradient(fmt, inverse):
+    """GDN(x + bias) in one kernel == PyTorch's add_(bias) followed by GDN, bit for bit; dbias == sum of dx."""
+    F = _F()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    shape = (3, 64, 18, 14)
+    C = shape[1]
+    x = (torch.randn(*shape, device="cuda", generator=g) * 2).contiguous(memory_format=fmt)
+    x[0, 0, 0, 0], x[0, 0, 0, 1], x[0, 1, 0, 0] = 0.0, -0.0, 1e-30
+    go = torch.randn(*shape, device="cuda", generator=g).contiguous(memory_format=fmt)
+    beta = torch.sqrt(torch.rand(C, device="cuda", generator=g) + 0.5).requires_grad_(True)
+    w = torch.sqrt(torch.rand(C, 1, 1, 1, device="cuda", generator=g) * 0.3 + 0.01).requires_grad_(True)
+    bias = (torch.randn(C, device="cuda", generator=g) * 0.3).requires_grad_(True)
+    bias.data[0] = 0.0
+    xa = x.clone().requires_grad_(True)
+    ya = F.gdn(xa, beta, w, inverse, bias=bias)
+    (ya * go).sum().backward()
+    ga = (xa.grad.clone(), beta.grad.clone(), w.grad.clone(), bias.grad.clone())
+    beta.grad = w.grad = bias.grad = None
+    xb = x.clone().requires_grad_(True)
+    yb = TP.gdn(xb + bias.view(1, -1, 1, 1), beta, w, inverse)
+    (yb * go).sum().backward()
+    assert torch.equal(ya, yb), float((ya - yb).abs().max())
+    for mine, ref in zip(ga, (xb.grad, beta.grad, w.grad, bias.grad)):
+        assert float((mine - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-7
+    assert float((ga[3] - ga[0].sum(dim=(0, 2, 3))).abs().max()) <= 1e-5 * float(ga[3].abs().max()) + 1e-6
