@@ -32,6 +32,9 @@ PROTOTYPES = {
     "sic_gdn_bwd_workspace_bytes": (_z, [_i, _i, _i]),
     "sic_gdn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "sic_gdn_dense_fwd": (_i, [_p, _p, _p, _l, _i, _i, _p, _p]),
+    "sic_ssim_tiles": (_l, [_i, _i]),
+    "sic_ssim_fwd": (_i, [_p, _p, _i, _i, _i, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p]),
+    "sic_ssim_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "sic_quantize_indices": (_i, [_p, _i, _l, _i, _i, _p, _p, _p, _p]),
     "sic_build_cdf_tables": (_i, [_i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p]),
     "sic_rans_encode_host": (_l, [_p, _l, _p, _i, _i, _l, _p, _l]),

@@ -1,0 +1,208 @@
+// N3: SSIM statistics of one MS-SSIM scale, fused forward + backward.
+//
+// The distortion of the reference's loss is 1 - piq.multi_scale_ssim(x_hat.clamp(0,1), x, data_range=1,
+// scale_weights=[.3,.5,.2]) (/root/reference/code/modelv2/model.py:93-102; piq 0.8.0 is third-party, its algorithm is
+// restated in losses.py — PARITY UNPINNED).  In eager PyTorch one scale is 5 depthwise 11x11 convolutions + ~15 elementwise
+// launches forward and about twice that backward; after GDN and the likelihood were fused this chain was the largest block
+// of the training step (ncu launch list r01: 30 % of kernel time).  Here, per scale:
+//   forward : one kernel — halo tile of x and y in shared memory, separable Gaussian (11+11 taps instead of 121) of
+//             x, y, x^2, y^2, xy, then per pixel  cs = (2 s_xy + c2)/(s_xx + s_yy + c2),  ss = (2 mu_x mu_y + c1)/(mu_x^2+mu_y^2+c1) * cs,
+//             per-CTA partial sums of ss and cs (folded in a fixed order by the host -> deterministic), and — when a
+//             gradient will be needed — five per-pixel maps from which any upstream (g_ss, g_cs) gradient is a linear mix;
+//   backward: one kernel — transposed (full) separable Gaussian of the three mixed maps, then
+//             dX = B_mu + 2 X B_xx + Y B_xy.
+// Data is tiny (3-channel images), so these kernels are launch/latency sized, not roofline material.
+#include "common.cuh"
+
+namespace sic {
+namespace {
+
+constexpr int kT = 32;            // output tile edge
+constexpr int kK = 11;            // Gaussian taps
+constexpr int kHalo = kT + kK - 1;  // 42
+constexpr int kThreads = 256;
+
+// normalised 1-D Gaussian, sigma 1.5, 11 taps (float32 values of exp(-d^2/4.5)/sum, as losses._gaussian_window builds them);
+// the 2-D window is its outer product
+__constant__ float c_g[kK] = {1.028380357e-03f, 7.598758209e-03f, 3.600077331e-02f, 1.093606874e-01f, 2.130055279e-01f, 2.660117149e-01f, 2.130055279e-01f, 1.093606874e-01f, 3.600077331e-02f, 7.598758209e-03f, 1.028380357e-03f};
+
+// ---- forward ---------------------------------------------------------------------------------------------------------
+// maps (nullable): [5][planes][Hv][Wv] = M2mu, M2xx, M2xy, l, T   (see ssim_bwd_kernel)
+__global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(const float *__restrict__ X, const float *__restrict__ Y, int H, int W,
+                                                            float c1, float c2, float *__restrict__ part_ss,
+                                                            float *__restrict__ part_cs, float *__restrict__ maps, long map_stride) {
+    __shared__ float sx[kHalo][kHalo + 1], sy[kHalo][kHalo + 1];
+    __shared__ float hb[5][kHalo][kT + 1];
+    __shared__ float red[2][kThreads / 32];
+    const int plane = blockIdx.z;
+    const int Hv = H - (kK - 1), Wv = W - (kK - 1);
+    const int oy0 = blockIdx.y * kT, ox0 = blockIdx.x * kT;
+    const float *xp = X + (long)plane * H * W, *yp = Y + (long)plane * H * W;
+    for (int i = threadIdx.x; i < kHalo * kHalo; i += kThreads) {
+        int r = i / kHalo, c = i - r * kHalo;
+        int gy = oy0 + r, gx = ox0 + c;
+        bool in = gy < H && gx < W;
+        sx[r][c] = in ? __ldg(xp + (long)gy * W + gx) : 0.f;
+        sy[r][c] = in ? __ldg(yp + (long)gy * W + gx) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHalo * kT; i += kThreads) {   // horizontal pass
+        int r = i / kT, c = i - r * kT;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kK; ++k) {
+            float g = c_g[k], xv = sx[r][c + k], yv = sy[r][c + k];
+            a0 = fmaf(g, xv, a0);
+            a1 = fmaf(g, yv, a1);
+            a2 = fmaf(g, xv * xv, a2);
+            a3 = fmaf(g, yv * yv, a3);
+            a4 = fmaf(g, xv * yv, a4);
+        }
+        hb[0][r][c] = a0; hb[1][r][c] = a1; hb[2][r][c] = a2; hb[3][r][c] = a3; hb[4][r][c] = a4;
+    }
+    __syncthreads();
+    float acc_ss = 0.f, acc_cs = 0.f;
+    for (int i = threadIdx.x; i < kT * kT; i += kThreads) {      // vertical pass + per-pixel SSIM terms
+        int r = i / kT, c = i - r * kT;
+        int oy = oy0 + r, ox = ox0 + c;
+        if (oy < Hv && ox < Wv) {
+            float mx = 0.f, my = 0.f, exx = 0.f, eyy = 0.f, exy = 0.f;
+#pragma unroll
+            for (int k = 0; k < kK; ++k) {
+                float g = c_g[k];
+                mx = fmaf(g, hb[0][r + k][c], mx);
+                my = fmaf(g, hb[1][r + k][c], my);
+                exx = fmaf(g, hb[2][r + k][c], exx);
+                eyy = fmaf(g, hb[3][r + k][c], eyy);
+                exy = fmaf(g, hb[4][r + k][c], exy);
+            }
+            float sxx = exx - mx * mx, syy = eyy - my * my, sxy = exy - mx * my;
+            float A1 = 2.f * mx * my + c1, A2 = mx * mx + my * my + c1;
+            float B1 = 2.f * sxy + c2, B2 = sxx + syy + c2;
+            float l = A1 / A2, cs = B1 / B2;
+            acc_ss += l * cs;
+            acc_cs += cs;
+            if (maps != nullptr) {
+                float iB2 = 1.0f / B2;
+                long o = (long)plane * Hv * Wv + (long)oy * Wv + ox;
+                maps[o] = 2.f * iB2 * (cs * mx - my);                       // M2mu : d(sum cs)/d mu_x
+                maps[map_stride + o] = -cs * iB2;                          // M2xx : d(sum cs)/d E[x^2]
+                maps[2 * map_stride + o] = 2.f * iB2;                      // M2xy : d(sum cs)/d E[xy]
+                maps[3 * map_stride + o] = l;
+                maps[4 * map_stride + o] = cs * 2.f * (my - l * mx) / A2;  // T    : cs * dl/d mu_x
+            }
+        }
+    }
+    acc_ss = warp_sum(acc_ss);
+    acc_cs = warp_sum(acc_cs);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = acc_ss; red[1][threadIdx.x >> 5] = acc_cs; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f, c = 0.f;
+        for (int w = 0; w < kThreads / 32; ++w) { s += red[0][w]; c += red[1][w]; }
+        long tiles = (long)gridDim.x * gridDim.y;
+        long t = (long)plane * tiles + (long)blockIdx.y * gridDim.x + blockIdx.x;
+        part_ss[t] = s;
+        part_cs[t] = c;
+    }
+}
+
+// ---- backward --------------------------------------------------------------------------------------------------------
+// F = g_ss[plane] * mean(ss) + g_cs[plane] * mean(cs).  With k = g_ss*l + g_cs (per pixel):
+//   M_mu = g_ss*T + k*M2mu ,  M_xx = k*M2xx ,  M_xy = k*M2xy          (all scaled by 1/n_valid)
+//   dF/dX(q) = sum_p G(p..q) M_mu(p) + 2 X(q) sum_p G M_xx(p) + Y(q) sum_p G M_xy(p)      (transposed window: q = p + tap)
+__global__ void __launch_bounds__(kThreads) ssim_bwd_kernel(const float *__restrict__ X, const float *__restrict__ Y,
+                                                            const float *__restrict__ maps, long map_stride,
+                                                            const float *__restrict__ g_ss, const float *__restrict__ g_cs, int H, int W,
+                                                            float *__restrict__ dX) {
+    __shared__ float sm[3][kHalo][kHalo + 1];
+    __shared__ float hb[3][kHalo][kT + 1];
+    const int plane = blockIdx.z;
+    const int Hv = H - (kK - 1), Wv = W - (kK - 1);
+    const int qy0 = blockIdx.y * kT, qx0 = blockIdx.x * kT;
+    const float inv_n = 1.0f / ((float)Hv * (float)Wv);
+    const float gs = (g_ss ? __ldg(g_ss + plane) : 0.f) * inv_n, gc = (g_cs ? __ldg(g_cs + plane) : 0.f) * inv_n;
+    const float *mp = maps + (long)plane * Hv * Wv;
+    for (int i = threadIdx.x; i < kHalo * kHalo; i += kThreads) {
+        int r = i / kHalo, c = i - r * kHalo;
+        int py = qy0 + r - (kK - 1), px = qx0 + c - (kK - 1);     // valid-map coordinate that reaches q with tap (kK-1 - ...)
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+        if (py >= 0 && py < Hv && px >= 0 && px < Wv) {
+            long o = (long)py * Wv + px;
+            float k = fmaf(gs, __ldg(mp + 3 * map_stride + o), gc);
+            m0 = fmaf(gs, __ldg(mp + 4 * map_stride + o), k * __ldg(mp + o));
+            m1 = k * __ldg(mp + map_stride + o);
+            m2 = k * __ldg(mp + 2 * map_stride + o);
+        }
+        sm[0][r][c] = m0; sm[1][r][c] = m1; sm[2][r][c] = m2;
+    }
+    __syncthreads();
+    // q = p + t  (t = tap index 0..10)  =>  p = q - t: halo column (c + 10 - t)
+    for (int i = threadIdx.x; i < kHalo * kT; i += kThreads) {
+        int r = i / kT, c = i - r * kT;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < kK; ++t) {
+            float g = c_g[t];
+            int cc = c + (kK - 1) - t;
+            a0 = fmaf(g, sm[0][r][cc], a0);
+            a1 = fmaf(g, sm[1][r][cc], a1);
+            a2 = fmaf(g, sm[2][r][cc], a2);
+        }
+        hb[0][r][c] = a0; hb[1][r][c] = a1; hb[2][r][c] = a2;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kT * kT; i += kThreads) {
+        int r = i / kT, c = i - r * kT;
+        int qy = qy0 + r, qx = qx0 + c;
+        if (qy < H && qx < W) {
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll
+            for (int t = 0; t < kK; ++t) {
+                float g = c_g[t];
+                int rr = r + (kK - 1) - t;
+                b0 = fmaf(g, hb[0][rr][c], b0);
+                b1 = fmaf(g, hb[1][rr][c], b1);
+                b2 = fmaf(g, hb[2][rr][c], b2);
+            }
+            long o = (long)plane * H * W + (long)qy * W + qx;
+            dX[o] = b0 + 2.f * __ldg(X + o) * b1 + __ldg(Y + o) * b2;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace sic
+
+using namespace sic;
+
+extern "C" long sic_ssim_tiles(int H, int W) {
+    if (H < 11 || W < 11) return 0;
+    return (long)((H - 10 + kT - 1) / kT) * ((W - 10 + kT - 1) / kT);
+}
+
+extern "C" int sic_ssim_fwd(const float *X, const float *Y, int planes, int H, int W, float c1, float c2, float *part_ss,
+                            float *part_cs, float *maps, void *stream) {
+    SIC_CHECK_ARG(planes > 0 && H >= 11 && W >= 11, "sic_ssim_fwd: needs planes > 0 and images of at least 11x11 (got %d, %dx%d)", planes, H, W);
+    SIC_CHECK_ARG(X && Y && part_ss && part_cs, "sic_ssim_fwd: null pointer");
+    SIC_CHECK_ARG(planes <= 65535, "sic_ssim_fwd: more than 65535 (batch x channel) planes");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Hv = H - 10, Wv = W - 10;
+    dim3 grid((Wv + kT - 1) / kT, (Hv + kT - 1) / kT, planes);
+    ssim_fwd_kernel<<<grid, kThreads, 0, st>>>(X, Y, H, W, c1, c2, part_ss, part_cs, maps, (long)planes * Hv * Wv);
+    SIC_CHECK_LAUNCH("sic_ssim_fwd");
+    return 0;
+}
+
+extern "C" int sic_ssim_bwd(const float *X, const float *Y, const float *maps, const float *g_ss, const float *g_cs, int planes,
+                            int H, int W, float *dX, void *stream) {
+    SIC_CHECK_ARG(planes > 0 && H >= 11 && W >= 11, "sic_ssim_bwd: bad extents");
+    SIC_CHECK_ARG(X && Y && maps && dX, "sic_ssim_bwd: null pointer");
+    SIC_CHECK_ARG(planes <= 65535, "sic_ssim_bwd: more than 65535 (batch x channel) planes");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Hv = H - 10, Wv = W - 10;
+    dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, planes);
+    ssim_bwd_kernel<<<grid, kThreads, 0, st>>>(X, Y, maps, (long)planes * Hv * Wv, g_ss, g_cs, H, W, dX);
+    SIC_CHECK_LAUNCH("sic_ssim_bwd");
+    return 0;
+}

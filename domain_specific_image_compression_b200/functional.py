@@ -280,6 +280,52 @@ def gdn_dense(x: torch.Tensor, beta_param: torch.Tensor, gamma_param: torch.Tens
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# N3: SSIM statistics of one MS-SSIM scale
+class _SSIMStats(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, c1: float, c2: float):
+        lib = _lib.load()
+        x = _require_cuda_f32(x, "x")
+        y = _require_cuda_f32(y, "y")
+        if x.shape != y.shape or x.dim() != 4:
+            raise _lib.SicError("ssim_stats expects two [B,C,H,W] tensors of the same shape")
+        B, C, H, W = x.shape
+        if H < 11 or W < 11:
+            raise ValueError("Kernel size can't be greater than actual input size.")
+        planes, tiles = B * C, lib.sic_ssim_tiles(H, W)
+        part = torch.empty((2, planes, tiles), dtype=torch.float32, device=x.device)
+        need = ctx.needs_input_grad[0]
+        maps = torch.empty((5, planes, H - 10, W - 10), dtype=torch.float32, device=x.device) if need else None
+        with torch.cuda.device(x.device):
+            _launch(lib.sic_ssim_fwd(_ptr(x), _ptr(y), planes, H, W, c1, c2, _ptr(part[0]), _ptr(part[1]), _ptr(maps), _stream()),
+                    "sic_ssim_fwd")
+        means = part.sum(dim=2) * (1.0 / ((H - 10) * (W - 10)))             # fixed-order fold of the per-tile partials
+        if need:
+            ctx.save_for_backward(x, y, maps)
+        ctx.set_materialize_grads(False)
+        return means[0].view(B, C), means[1].view(B, C)
+
+    @staticmethod
+    def backward(ctx, g_ss, g_cs):
+        lib = _lib.load()
+        x, y, maps = ctx.saved_tensors
+        B, C, H, W = x.shape
+        g_ss = None if g_ss is None else _require_cuda_f32(g_ss, "g_ss")
+        g_cs = None if g_cs is None else _require_cuda_f32(g_cs, "g_cs")
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _launch(lib.sic_ssim_bwd(_ptr(x), _ptr(y), _ptr(maps), _ptr(g_ss), _ptr(g_cs), B * C, H, W, _ptr(dx), _stream()),
+                    "sic_ssim_bwd")
+        return dx, None, None, None
+
+
+def ssim_stats(x: torch.Tensor, y: torch.Tensor, c1: float = 0.01 ** 2, c2: float = 0.03 ** 2):
+    """Per-(batch, channel) means of the SSIM map and of its contrast-structure factor for one scale: (ss [B,C], cs [B,C]).
+    Differentiable w.r.t. x only (y is the target)."""
+    return _SSIMStats.apply(x, y, float(c1), float(c2))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # K4 / K3 / E1
 def quantize_indices(q: torch.Tensor, do_round: bool = False, tail: int = 10, want_symbols: bool = True):
     """Per-patch support and symbols (K4): returns (sym int32 like q, mins int32 [B], maxs int32 [B]) on the device."""

@@ -32,6 +32,11 @@ def _ssim_and_cs(x, y, win, c1, c2):
     return ss.mean(dim=(-1, -2)), cs.mean(dim=(-1, -2))     # [B,C] each
 
 
+def _fused_ok(x, y, kernel_size, kernel_sigma):
+    return (x.is_cuda and y.is_cuda and x.dtype == torch.float32 and kernel_size == 11 and kernel_sigma == 1.5
+            and not y.requires_grad and x.size(0) * x.size(1) <= 65535)
+
+
 def multi_scale_ssim(x, y, data_range=1.0, scale_weights=None, kernel_size=11, kernel_sigma=1.5, k1=0.01, k2=0.03):
     if scale_weights is None:
         scale_weights = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], device=x.device, dtype=x.dtype)
@@ -44,7 +49,8 @@ def multi_scale_ssim(x, y, data_range=1.0, scale_weights=None, kernel_size=11, k
         raise ValueError(f"Invalid size of the input images, expected at least {min_size}x{min_size}.")
     x = x / float(data_range)
     y = y / float(data_range)
-    win = _gaussian_window(kernel_size, kernel_sigma, x.device, x.dtype).repeat(x.size(1), 1, 1, 1)
+    fused = _fused_ok(x, y, kernel_size, kernel_sigma)       # CUDA tensors: one fused kernel per scale (csrc/msssim.cu)
+    win = None if fused else _gaussian_window(kernel_size, kernel_sigma, x.device, x.dtype).repeat(x.size(1), 1, 1, 1)
     c1, c2 = k1 ** 2, k2 ** 2
     terms = []
     ssim_last = None
@@ -53,7 +59,11 @@ def multi_scale_ssim(x, y, data_range=1.0, scale_weights=None, kernel_size=11, k
             pad = max(x.shape[2] % 2, x.shape[3] % 2)
             x = F.avg_pool2d(F.pad(x, [pad, 0, pad, 0], mode="replicate"), kernel_size=2, padding=0)
             y = F.avg_pool2d(F.pad(y, [pad, 0, pad, 0], mode="replicate"), kernel_size=2, padding=0)
-        ssim_last, cs = _ssim_and_cs(x, y, win, c1, c2)
+        if fused:
+            from . import functional as F_sic
+            ssim_last, cs = F_sic.ssim_stats(x, y, c1, c2)
+        else:
+            ssim_last, cs = _ssim_and_cs(x, y, win, c1, c2)
         terms.append(cs)
     stacked = torch.relu(torch.stack(terms[:-1] + [ssim_last], dim=0))          # [levels,B,C]
     powered = stacked ** scale_weights.view(-1, 1, 1)

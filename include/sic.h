@@ -120,6 +120,19 @@ int sic_build_cdf_tables(int kind, const float *sigma, const float *nu, int n_ro
                          const int32_t *mins, const int32_t *maxs, int stride, uint16_t *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * N3  SSIM statistics of ONE scale of the MS-SSIM distortion (model.py:93-102 calls piq.multi_scale_ssim; 11x11 Gaussian
+ * window sigma 1.5, "valid" support, k1=.01, k2=.03 -> c1 = 1e-4, c2 = 9e-4 at data_range 1).
+ *   X (reconstruction, clamped), Y (target): [planes, H, W] contiguous, planes = B*C.
+ *   fwd: part_ss / part_cs [planes * sic_ssim_tiles(H,W)] per-tile sums of the ss and cs maps over the valid region (the host
+ *        folds them and divides by (H-10)(W-10)); maps (nullable) [5, planes, H-10, W-10]: what bwd needs.
+ *   bwd: dX = d(g_ss[plane]*mean(ss) + g_cs[plane]*mean(cs))/dX ; g_ss / g_cs [planes], either may be NULL (= 0). */
+long sic_ssim_tiles(int H, int W);
+int sic_ssim_fwd(const float *X, const float *Y, int planes, int H, int W, float c1, float c2, float *part_ss, float *part_cs,
+                 float *maps, void *stream);
+int sic_ssim_bwd(const float *X, const float *Y, const float *maps, const float *g_ss, const float *g_cs, int planes, int H,
+                 int W, float *dX, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * E1  entropy coder, format SIC-RANS-1 (replaces torchac.encode_float_cdf / decode_float_cdf at
  * eval_selfcontained_entropy.py:48,62,96,116).  HOST buffers.  One call = one stream (one patch, one latent).
  *   sym [n] int32 in [0,L); tables [n/sym_per_row rows, stride] uint16; returns bytes written (>=0) or SIC_E_*. */

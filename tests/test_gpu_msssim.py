@@ -1,0 +1,59 @@
+"""N3: fused SSIM-statistics kernels (one forward + one backward launch per MS-SSIM scale) against the PyTorch statement
+of the same algorithm (losses._ssim_and_cs: depthwise conv2d chain) and a float64 numpy evaluation."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    from domain_specific_image_compression_b200 import functional as F
+    from domain_specific_image_compression_b200 import losses
+    return F, losses
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 64), (1, 3, 41, 53), (3, 1, 11, 11), (2, 3, 128, 96)])
+def test_ssim_stats_forward_backward_vs_conv_chain(shape):
+    F, losses = _mods()
+    g = torch.Generator(device="cuda").manual_seed(sum(shape))
+    y = torch.rand(*shape, device="cuda", generator=g)
+    x0 = (y + 0.15 * torch.randn(*shape, device="cuda", generator=g)).clamp(0, 1)
+    gs, gc = torch.randn(shape[0], shape[1], device="cuda", generator=g), torch.randn(shape[0], shape[1], device="cuda", generator=g)
+    xa = x0.clone().requires_grad_(True)
+    ss, cs = F.ssim_stats(xa, y)
+    ((ss * gs).sum() + (cs * gc).sum()).backward()
+    xb = x0.double().clone().requires_grad_(True)
+    win = losses._gaussian_window(11, 1.5, x0.device, torch.float64).repeat(shape[1], 1, 1, 1)
+    ss_r, cs_r = losses._ssim_and_cs(xb, y.double(), win, 0.01 ** 2, 0.03 ** 2)
+    ((ss_r * gs.double()).sum() + (cs_r * gc.double()).sum()).backward()
+    assert float((ss.double() - ss_r).abs().max()) < 2e-6 and float((cs.double() - cs_r).abs().max()) < 2e-6
+    assert float((xa.grad.double() - xb.grad).abs().max()) <= 2e-5 * float(xb.grad.abs().max()) + 1e-9
+    with pytest.raises(ValueError):
+        F.ssim_stats(torch.rand(1, 3, 10, 30, device="cuda"), torch.rand(1, 3, 10, 30, device="cuda"))
+
+
+def test_multi_scale_ssim_fused_equals_unfused(monkeypatch):
+    F, losses = _mods()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    y = torch.rand(4, 3, 256, 256, device="cuda", generator=g)
+    x0 = (y + 0.1 * torch.randn(4, 3, 256, 256, device="cuda", generator=g))
+    w = torch.tensor([0.3, 0.5, 0.2], device="cuda")
+    xa = x0.clone().requires_grad_(True)
+    n0 = F.launch_count
+    va = losses.multi_scale_ssim(xa.clamp(0, 1), y, 1.0, w)
+    va.backward()
+    assert F.launch_count - n0 == 6                         # 3 scales x (1 forward + 1 backward kernel)
+    monkeypatch.setattr(losses, "_fused_ok", lambda *a, **k: False)
+    xb = x0.clone().requires_grad_(True)
+    vb = losses.multi_scale_ssim(xb.clamp(0, 1), y, 1.0, w)
+    vb.backward()
+    assert abs(float(va) - float(vb)) < 2e-6
+    assert float((xa.grad - xb.grad).abs().max()) <= 1e-4 * float(xb.grad.abs().max()) + 1e-10
+    # identical images -> 1, and the channels_last / odd-size (replicate-padded pooling) paths run
+    assert abs(float(losses.multi_scale_ssim(y, y, 1.0, w)) - 1.0) < 1e-6
+    z = torch.rand(2, 3, 101, 77, device="cuda", generator=g)
+    a = losses.multi_scale_ssim(z.contiguous(memory_format=torch.channels_last), z * 0.9, 1.0, w)
+    monkeypatch.undo()
+    b = losses.multi_scale_ssim(z, z * 0.9, 1.0, w)
+    assert abs(float(a) - float(b)) < 2e-6
