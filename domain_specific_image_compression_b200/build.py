@@ -31,6 +31,7 @@ SOURCES = [
     ("msssim.cu", []),
     ("tables.cu", ["-fmad=false"]),
     ("rans_host.cpp", []),
+    ("rans_device.cu", []),
 ]
 
 

@@ -1,0 +1,192 @@
+// N1 / E1 on the GPU: interleaved rANS encoder / decoder, format SIC-RANS-1 — byte-identical to rans_host.cpp.
+//
+// Replaces the CPU coder + per-patch device->host copies of /root/reference/code/modelv2/eval_selfcontained_entropy.py
+// :48,62 (encode) and :96,116 (decode), where torchac runs serially on the host for every patch and stream.
+// One WARP per stream (one patch, one latent): lane l owns the symbols i with i mod 32 == l — exactly the 32 interleaved
+// lanes of the format — so an iteration codes 32 symbols at once, and the only serial dependence is the word cursor,
+// which advances by a warp ballot + popcount.  All patches of a batch run concurrently (patches are independent).
+//   encoder: walks the iterations backwards and fills the word area from its END, lane ranks descending, which is the
+//            reversed emission order the format prescribes; then slides the words down behind the 32 state words.
+//   decoder: walks forwards; a lane that drops below 2^16 pulls the next word, rank = popc(ballot & lanes below).
+// Table rows (uint16, possibly with zero-width symbols) are widened on the fly exactly like the host coder:
+//   c'_k = floor(c_k (65536 - L) / 65535) + k.   In broadcast mode (one row per channel) the row in use is staged in
+// shared memory, so the decoder's binary search runs there.
+#include "common.cuh"
+
+namespace sic {
+namespace {
+
+constexpr int kWarps = 4;  // streams per CTA
+constexpr uint32_t kLow = 1u << 16;
+constexpr int kMaxL = 4096;
+
+__device__ __forceinline__ uint32_t widen(uint32_t c, uint32_t k, uint32_t L) { return c * (65536u - L) / 65535u + k; }
+
+__global__ void __launch_bounds__(kWarps * 32) rans_encode_kernel(const int32_t *__restrict__ sym, const uint16_t *__restrict__ tables,
+                                                                  const int32_t *__restrict__ Ls, int n_streams, long n,
+                                                                  long sym_per_row, long rows_per_stream, int stride, uint8_t *out,
+                                                                  long cap, int32_t *__restrict__ out_nbytes) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * kWarps + warp;
+    if (s >= n_streams) return;
+    const uint32_t L = (uint32_t)Ls[s];
+    const int32_t *sy = sym + (long)s * n;
+    const uint16_t *tab = tables + (long)s * rows_per_stream * stride;
+    uint8_t *o = out + (long)s * cap;
+    uint16_t *words = reinterpret_cast<uint16_t *>(o + 128);
+    const long wcap = (cap - 128) / 2;
+    long pos = wcap;  // words are written at [pos, wcap), growing downwards
+    uint32_t x = kLow;
+    bool bad = false;
+    const long iters = (n + 31) / 32;
+    for (long j = iters - 1; j >= 0; --j) {
+        const long i = j * 32 + lane;
+        bool emit = false;
+        uint32_t word = 0;
+        if (i < n) {
+            int32_t v = sy[i];
+            if (v < 0 || (uint32_t)v >= L) { bad = true; v = 0; }
+            const uint16_t *row = tab + (i / sym_per_row) * stride;
+            uint32_t c0 = widen(row[v], (uint32_t)v, L), c1 = widen(row[v + 1], (uint32_t)v + 1, L);
+            uint32_t f = c1 - c0;
+            if (x >= (f << 16)) { emit = true; word = x & 0xffffu; x >>= 16; }
+            x = ((x / f) << 16) + (x % f) + c0;
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, emit);
+        int cnt = __popc(mask);
+        if (emit) {
+            int rank = __popc(mask & ((1u << lane) - 1u));   // lanes below me come earlier in decode order
+            long at = pos - cnt + rank;
+            if (at >= 0) words[at] = (uint16_t)word;
+        }
+        pos -= cnt;
+    }
+    bad = __any_sync(0xffffffffu, bad) || pos < 0;
+    // 32 final states first (lane 0 first), little endian
+    reinterpret_cast<uint32_t *>(o)[lane] = x;
+    // slide the words down so that they follow the states: dst index w <- src index pos + w  (dst < src, ascending order is safe)
+    const long nw = wcap - (pos < 0 ? 0 : pos);
+    for (long w0 = 0; w0 < nw; w0 += 32) {
+        long w = w0 + lane;
+        uint16_t v = 0;
+        if (w < nw) v = words[pos + w];
+        __syncwarp();
+        if (w < nw) words[w] = v;
+        __syncwarp();
+    }
+    if (lane == 0) out_nbytes[s] = bad ? -1 : (int32_t)(128 + 2 * nw);
+}
+
+__global__ void __launch_bounds__(kWarps * 32) rans_decode_kernel(const uint8_t *__restrict__ in, const int32_t *__restrict__ nbytes,
+                                                                  const uint16_t *__restrict__ tables, const int32_t *__restrict__ Ls,
+                                                                  int n_streams, long n, long sym_per_row, long rows_per_stream,
+                                                                  int stride, long cap, int32_t *__restrict__ sym,
+                                                                  int32_t *__restrict__ status) {
+    extern __shared__ uint32_t srow_all[];  // [kWarps][stride] widened row of the channel in flight (broadcast mode)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * kWarps + warp;
+    if (s >= n_streams) return;
+    uint32_t *srow = srow_all + (size_t)warp * stride;
+    const uint32_t L = (uint32_t)Ls[s];
+    const long nb = nbytes[s];
+    const uint8_t *ip = in + (long)s * cap;
+    const uint16_t *words = reinterpret_cast<const uint16_t *>(ip + 128);
+    const long nw = nb >= 128 ? (nb - 128) / 2 : 0;
+    const uint16_t *tab = tables + (long)s * rows_per_stream * stride;
+    int32_t *so = sym + (long)s * n;
+    if (nb < 128) {
+        if (lane == 0) status[s] = SIC_E_TRUNCATED;
+        return;
+    }
+    uint32_t x = reinterpret_cast<const uint32_t *>(ip)[lane];
+    long pos = 0;
+    bool trunc = false;
+    const bool staged = sym_per_row % 32 == 0;   // then the 32 symbols of an iteration share one row
+    long cur_row = -1;
+    const long iters = (n + 31) / 32;
+    for (long j = 0; j < iters; ++j) {
+        const long i = j * 32 + lane;
+        if (staged) {
+            long r = (j * 32) / sym_per_row;
+            if (r != cur_row) {
+                __syncwarp();
+                const uint16_t *row = tab + r * stride;
+                for (uint32_t k = lane; k <= L; k += 32) srow[k] = widen(row[k], k, L);
+                cur_row = r;
+                __syncwarp();
+            }
+        }
+        bool need = false;
+        if (i < n) {
+            const uint32_t slot = x & 0xffffu;
+            uint32_t lo = 0, hi = L, c0, c1;
+            if (staged) {
+                while (hi - lo > 1) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (srow[mid] <= slot) lo = mid; else hi = mid;
+                }
+                c0 = srow[lo];
+                c1 = srow[lo + 1];
+            } else {
+                const uint16_t *row = tab + (i / sym_per_row) * stride;
+                while (hi - lo > 1) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (widen(row[mid], mid, L) <= slot) lo = mid; else hi = mid;
+                }
+                c0 = widen(row[lo], lo, L);
+                c1 = widen(row[lo + 1], lo + 1, L);
+            }
+            x = (c1 - c0) * (x >> 16) + slot - c0;
+            need = x < kLow;
+            so[i] = (int32_t)lo;
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (need) {
+            long at = pos + __popc(mask & ((1u << lane) - 1u));
+            if (at < nw) x = (x << 16) | (uint32_t)words[at];
+            else trunc = true;
+        }
+        pos += __popc(mask);
+    }
+    trunc = __any_sync(0xffffffffu, trunc);
+    if (lane == 0) status[s] = trunc ? SIC_E_TRUNCATED : 0;
+}
+
+}  // namespace
+}  // namespace sic
+
+using namespace sic;
+
+extern "C" int sic_rans_encode(const int32_t *sym, const uint16_t *tables, const int32_t *Ls, int n_streams, long n,
+                               long sym_per_row, long rows_per_stream, int stride, uint8_t *out, long cap, int32_t *out_nbytes,
+                               void *stream) {
+    SIC_CHECK_ARG(n_streams > 0 && n >= 0 && sym_per_row > 0 && rows_per_stream > 0 && stride >= 2, "sic_rans_encode: bad extents");
+    SIC_CHECK_ARG(sym && tables && Ls && out && out_nbytes, "sic_rans_encode: null pointer");
+    SIC_CHECK_ARG(cap >= 128 + 2 * n && cap % 4 == 0, "sic_rans_encode: cap must be a multiple of 4 and >= 128 + 2n (= %ld)", 128 + 2 * n);
+    SIC_CHECK_ARG(((uintptr_t)out & 3) == 0, "sic_rans_encode: out must be 4-byte aligned");
+    rans_encode_kernel<<<(n_streams + kWarps - 1) / kWarps, kWarps * 32, 0, (cudaStream_t)stream>>>(
+        sym, tables, Ls, n_streams, n, sym_per_row, rows_per_stream, stride, out, cap, out_nbytes);
+    SIC_CHECK_LAUNCH("sic_rans_encode");
+    return 0;
+}
+
+extern "C" int sic_rans_decode(const uint8_t *in, const int32_t *nbytes, const uint16_t *tables, const int32_t *Ls, int n_streams,
+                               long n, long sym_per_row, long rows_per_stream, int stride, long cap, int32_t *sym, int32_t *status,
+                               void *stream) {
+    SIC_CHECK_ARG(n_streams > 0 && n >= 0 && sym_per_row > 0 && rows_per_stream > 0 && stride >= 2 && stride <= kMaxL + 1,
+                  "sic_rans_decode: bad extents");
+    SIC_CHECK_ARG(in && nbytes && tables && Ls && sym && status, "sic_rans_decode: null pointer");
+    SIC_CHECK_ARG(cap % 4 == 0 && ((uintptr_t)in & 3) == 0, "sic_rans_decode: streams must be 4-byte aligned (cap %% 4 == 0)");
+    size_t smem = (size_t)kWarps * stride * sizeof(uint32_t);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rans_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("sic_rans_decode: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+            return (int)e;
+        }
+    }
+    rans_decode_kernel<<<(n_streams + kWarps - 1) / kWarps, kWarps * 32, smem, (cudaStream_t)stream>>>(
+        in, nbytes, tables, Ls, n_streams, n, sym_per_row, rows_per_stream, stride, cap, sym, status);
+    SIC_CHECK_LAUNCH("sic_rans_decode");
+    return 0;
+}

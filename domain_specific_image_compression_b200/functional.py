@@ -392,3 +392,37 @@ def rans_decode(data: bytes, n: int, tables: np.ndarray, L: int, sym_per_row: in
     _lib.check(lib.sic_rans_decode_host(buf.ctypes.data, buf.size, int(n), tables.ctypes.data, tables.shape[-1], int(L),
                                         int(sym_per_row), sym.ctypes.data), "sic_rans_decode_host")
     return sym
+
+
+def rans_encode_device(sym: torch.Tensor, tables: torch.Tensor, Ls: torch.Tensor, sym_per_row: int, rows_per_stream: int):
+    """GPU rANS encoder (N1): sym int32 [S, n], tables uint16 [S*rows_per_stream, stride], Ls int32 [S] — all on the device.
+    Returns (bytes uint8 [S, cap], nbytes int32 [S]) on the device; one warp per stream, byte-identical to the host coder."""
+    lib = _lib.load()
+    if not (sym.is_cuda and sym.dtype == torch.int32 and tables.dtype == torch.uint16 and Ls.dtype == torch.int32):
+        raise _lib.SicError("rans_encode_device: expected CUDA int32 symbols, uint16 tables, int32 Ls")
+    S = sym.shape[0]
+    n = sym.numel() // S
+    sym, tables, Ls = sym.contiguous(), tables.contiguous(), Ls.contiguous()
+    cap = (128 + 2 * n + 3) // 4 * 4
+    out = torch.empty((S, cap), dtype=torch.uint8, device=sym.device)
+    nbytes = torch.empty(S, dtype=torch.int32, device=sym.device)
+    with torch.cuda.device(sym.device):
+        _launch(lib.sic_rans_encode(_ptr(sym), _ptr(tables), _ptr(Ls), S, n, int(sym_per_row), int(rows_per_stream), tables.shape[-1],
+                                    _ptr(out), cap, _ptr(nbytes), _stream()), "sic_rans_encode")
+    return out, nbytes
+
+
+def rans_decode_device(data: torch.Tensor, nbytes: torch.Tensor, tables: torch.Tensor, Ls: torch.Tensor, n: int, sym_per_row: int,
+                       rows_per_stream: int):
+    """GPU rANS decoder (N1): data uint8 [S, cap] (cap % 4 == 0), nbytes int32 [S]; returns (sym int32 [S, n], status int32 [S])."""
+    lib = _lib.load()
+    S, cap = data.shape
+    if not (data.is_cuda and data.dtype == torch.uint8 and nbytes.dtype == torch.int32 and cap % 4 == 0):
+        raise _lib.SicError("rans_decode_device: expected CUDA uint8 [S, cap] with cap % 4 == 0 and int32 nbytes")
+    data, tables, Ls, nbytes = data.contiguous(), tables.contiguous(), Ls.contiguous(), nbytes.contiguous()
+    sym = torch.empty((S, n), dtype=torch.int32, device=data.device)
+    status = torch.empty(S, dtype=torch.int32, device=data.device)
+    with torch.cuda.device(data.device):
+        _launch(lib.sic_rans_decode(_ptr(data), _ptr(nbytes), _ptr(tables), _ptr(Ls), S, int(n), int(sym_per_row), int(rows_per_stream),
+                                    tables.shape[-1], cap, _ptr(sym), _ptr(status), _stream()), "sic_rans_decode")
+    return sym, status

@@ -77,9 +77,13 @@ class CompressionModel(nn.Module):
 
     # ------------------------------------------------------------------------------------------------ entropy coding
     @torch.no_grad()
-    def compress(self, x, tail=10):
-        """custom_compress (eval_selfcontained_entropy.py:26-74): same return dict.  One host sync for the whole batch
-        (the reference has four per patch); tables are compact [B,C,L+1] instead of replicated over (h,w)."""
+    def compress(self, x, tail=10, coder="gpu"):
+        """custom_compress (eval_selfcontained_entropy.py:26-74): same return dict.
+        One host sync for the whole batch (the reference has four per patch); compact [B,C,L+1] tables instead of tables
+        replicated over (h,w); coder='gpu' codes every stream of the batch concurrently on the device (one warp per stream),
+        coder='host' uses the C++ coder — both emit identical bytes (format SIC-RANS-1)."""
+        if coder not in ("gpu", "host"):
+            raise ValueError("coder must be 'gpu' or 'host'")
         was_training = self.training
         self.eval()
         try:
@@ -96,16 +100,21 @@ class CompressionModel(nn.Module):
         tab_z = F_sic.build_cdf_tables("gaussian", self.z_prior.log_sigma.detach(), None, B, min_z, max_z, int((mxz - mnz).max()) + 2)
         sig, nu = self._table_params(out["sigma"], out["nu"])
         tab_y = F_sic.build_cdf_tables("studentt", sig, nu, B, min_y, max_y, int((mxy - mny).max()) + 2, channels=y_q.size(1))
-        sym_z_h, sym_y_h = sym_z.cpu().numpy(), sym_y.cpu().numpy()
-        tab_z_h = tab_z.cpu().numpy().reshape(B, -1, tab_z.shape[-1])
-        tab_y_h = tab_y.cpu().numpy().reshape(B, -1, tab_y.shape[-1])
         spr_z = z_q.size(2) * z_q.size(3)
         spr_y = 1 if self.spatial_params else y_q.size(2) * y_q.size(3)
-        strings = []
-        for b in range(B):
-            zs = F_sic.rans_encode(sym_z_h[b], tab_z_h[b], int(mxz[b] - mnz[b] + 1), spr_z)
-            ys = F_sic.rans_encode(sym_y_h[b], tab_y_h[b], int(mxy[b] - mny[b] + 1), spr_y)
-            strings.append([zs, ys])
+        if coder == "gpu":
+            bz, nz = F_sic.rans_encode_device(sym_z.view(B, -1), tab_z, max_z - min_z + 1, spr_z, tab_z.shape[0] // B)
+            by, ny = F_sic.rans_encode_device(sym_y.view(B, -1), tab_y, max_y - min_y + 1, spr_y, tab_y.shape[0] // B)
+            bz, nz, by, ny = bz.cpu().numpy(), nz.cpu().numpy(), by.cpu().numpy(), ny.cpu().numpy()
+            if (nz < 0).any() or (ny < 0).any():
+                raise F_sic._lib.SicError("rANS encoder: symbol outside its table support")
+            strings = [[bz[b, :nz[b]].tobytes(), by[b, :ny[b]].tobytes()] for b in range(B)]
+        else:
+            sym_z_h, sym_y_h = sym_z.cpu().numpy(), sym_y.cpu().numpy()
+            tab_z_h = tab_z.cpu().numpy().reshape(B, -1, tab_z.shape[-1])
+            tab_y_h = tab_y.cpu().numpy().reshape(B, -1, tab_y.shape[-1])
+            strings = [[F_sic.rans_encode(sym_z_h[b], tab_z_h[b], int(mxz[b] - mnz[b] + 1), spr_z),
+                        F_sic.rans_encode(sym_y_h[b], tab_y_h[b], int(mxy[b] - mny[b] + 1), spr_y)] for b in range(B)]
         return {"strings": strings, "shape_y": list(y_q.shape), "shape_z": list(z_q.shape),
                 "min_y": [int(v) for v in mny], "max_y": [int(v) for v in mxy],
                 "min_z": [int(v) for v in mnz], "max_z": [int(v) for v in mxz]}
@@ -115,9 +124,41 @@ class CompressionModel(nn.Module):
             return sigma.contiguous().view(-1), nu.contiguous().view(-1)
         return sigma[:, :, 0, 0].contiguous().view(-1), nu[:, :, 0, 0].contiguous().view(-1)
 
+    @staticmethod
+    def _pack_streams(strings, which, n_sym, device):
+        """byte strings of one latent -> uint8 [B, cap] (zero padded, cap % 4 == 0) + int32 lengths, on the device."""
+        B = len(strings)
+        cap = (max(128 + 2 * n_sym, max(len(s[which]) for s in strings)) + 3) // 4 * 4
+        buf = np.zeros((B, cap), np.uint8)
+        lens = np.zeros(B, np.int32)
+        for b in range(B):
+            raw = np.frombuffer(strings[b][which], np.uint8)
+            buf[b, :raw.size] = raw
+            lens[b] = raw.size
+        return torch.from_numpy(buf).to(device), torch.from_numpy(lens).to(device)
+
+    def _decode(self, strings, which, n_sym, tables, mins, maxs, spr, coder, dev):
+        """-> float32 latent [B, n_sym] on the device (symbol + min, eval_selfcontained_entropy.py:97,117)."""
+        B = len(strings)
+        if coder == "gpu":
+            data, lens = self._pack_streams(strings, which, n_sym, dev)
+            mins_d, maxs_d = torch.from_numpy(mins).to(dev), torch.from_numpy(maxs).to(dev)
+            sym, status = F_sic.rans_decode_device(data, lens, tables, maxs_d - mins_d + 1, n_sym, spr, tables.shape[0] // B)
+            if int(status.abs().max()) != 0:                                  # one sync; erasures must not pass silently
+                raise F_sic._lib.SicError("rANS decoder: truncated stream")
+            return (sym + mins_d.view(B, 1)).to(torch.float32)
+        tab_h = tables.cpu().numpy().reshape(B, -1, tables.shape[-1])
+        lat = np.empty((B, n_sym), np.float32)
+        for b in range(B):
+            s = F_sic.rans_decode(strings[b][which], n_sym, tab_h[b], int(maxs[b] - mins[b] + 1), spr)
+            lat[b] = (s + mins[b]).astype(np.float32)
+        return torch.from_numpy(lat).to(dev)
+
     @torch.no_grad()
-    def decompress(self, compressed):
+    def decompress(self, compressed, coder="gpu"):
         """custom_decompress (eval_selfcontained_entropy.py:76-123): returns x_hat.clamp(0,1) [B,3,H,W]."""
+        if coder not in ("gpu", "host"):
+            raise ValueError("coder must be 'gpu' or 'host'")
         dev = next(self.parameters()).device
         strings = compressed["strings"]
         shape_y, shape_z = list(compressed["shape_y"]), list(compressed["shape_z"])
@@ -126,14 +167,9 @@ class CompressionModel(nn.Module):
         mny, mxy = np.asarray(compressed["min_y"], np.int32), np.asarray(compressed["max_y"], np.int32)
         to_dev = lambda a: torch.from_numpy(a).to(dev)
         tab_z = F_sic.build_cdf_tables("gaussian", self.z_prior.log_sigma.detach(), None, B, to_dev(mnz), to_dev(mxz),
-                                       int((mxz - mnz).max()) + 2)
-        tab_z_h = tab_z.cpu().numpy().reshape(B, -1, tab_z.shape[-1])
+                                       int((mxz - mnz).max()) + 2)                                      # :88-94
         n_z = shape_z[1] * shape_z[2] * shape_z[3]
-        z_hat = np.empty((B, n_z), np.float32)
-        for b in range(B):
-            s = F_sic.rans_decode(strings[b][0], n_z, tab_z_h[b], int(mxz[b] - mnz[b] + 1), shape_z[2] * shape_z[3])
-            z_hat[b] = (s + mnz[b]).astype(np.float32)                       # :97
-        z_hat = to_dev(z_hat).view(B, *shape_z[1:])
+        z_hat = self._decode(strings, 0, n_z, tab_z, mnz, mxz, shape_z[2] * shape_z[3], coder, dev).view(B, *shape_z[1:])
         like = torch.empty(B, *shape_y[1:], device=dev)
         was_training = self.training
         self.eval()
@@ -142,15 +178,11 @@ class CompressionModel(nn.Module):
                 _, _, sigma, nu = self._student_params(z_hat, like)           # :99-106
                 sig, nu = self._table_params(sigma, nu)
                 tab_y = F_sic.build_cdf_tables("studentt", sig, nu, B, to_dev(mny), to_dev(mxy), int((mxy - mny).max()) + 2,
-                                               channels=shape_y[1])
-                tab_y_h = tab_y.cpu().numpy().reshape(B, -1, tab_y.shape[-1])
+                                               channels=shape_y[1])           # :108-114
                 n_y = shape_y[1] * shape_y[2] * shape_y[3]
                 spr_y = 1 if self.spatial_params else shape_y[2] * shape_y[3]
-                y_hat = np.empty((B, n_y), np.float32)
-                for b in range(B):
-                    s = F_sic.rans_decode(strings[b][1], n_y, tab_y_h[b], int(mxy[b] - mny[b] + 1), spr_y)
-                    y_hat[b] = (s + mny[b]).astype(np.float32)               # :117
-                x_hat = self.g_s(to_dev(y_hat).view(B, *shape_y[1:]))         # :119-120
+                y_hat = self._decode(strings, 1, n_y, tab_y, mny, mxy, spr_y, coder, dev).view(B, *shape_y[1:])
+                x_hat = self.g_s(y_hat)                                       # :119-120
         finally:
             self.train(was_training)
         return x_hat.clamp(0, 1)                                             # :123

@@ -141,6 +141,16 @@ long sic_rans_encode_host(const int32_t *sym, long n, const uint16_t *tables, in
 int sic_rans_decode_host(const uint8_t *in, long nbytes, long n, const uint16_t *tables, int stride, int L,
                          long sym_per_row, int32_t *sym);
 
+
+/* N1  the same coder on the GPU: one warp per stream, all streams of a batch concurrently; bytes identical to the host coder.
+ *   sym [n_streams, n] int32; tables [n_streams * rows_per_stream, stride] uint16; Ls [n_streams] int32 (symbols per
+ *   stream's support); out [n_streams, cap] with cap >= 128 + 2n, cap % 4 == 0; out_nbytes [n_streams] (-1: symbol out of
+ *   range).  decode: status [n_streams] = 0 or SIC_E_TRUNCATED.  All pointers are DEVICE pointers. */
+int sic_rans_encode(const int32_t *sym, const uint16_t *tables, const int32_t *Ls, int n_streams, long n, long sym_per_row,
+                    long rows_per_stream, int stride, uint8_t *out, long cap, int32_t *out_nbytes, void *stream);
+int sic_rans_decode(const uint8_t *in, const int32_t *nbytes, const uint16_t *tables, const int32_t *Ls, int n_streams, long n,
+                    long sym_per_row, long rows_per_stream, int stride, long cap, int32_t *sym, int32_t *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
