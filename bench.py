@@ -285,7 +285,13 @@ def run_ours(args):
         }
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing a process group down while a captured CUDA graph still references its NCCL kernels can hang
+        # (observed at 8 ranks: the JSON line was out, then destroy_process_group() never returned).  Everything has been
+        # measured and printed: synchronise, meet the other ranks once more, and leave without running the teardown.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def kernel_rooflines(cfg, dev):
