@@ -335,7 +335,15 @@ def kernel_rooflines(cfg, dev):
     y = F.gdn(xr, beta, w, False)
     t = time_it(lambda: torch.autograd.grad(y, (xr, beta, w), g, retain_graph=True))
     out["gdn_bwd"] = {"shape": list(x.shape), "bytes": 12 * n, "ms": t * 1e3, "gbs": 12 * n / t / 1e9}
-    del x, g, xr, y
+    xc = x.contiguous(memory_format=torch.channels_last)
+    gc = g.contiguous(memory_format=torch.channels_last)
+    t = time_it(lambda: F.gdn(xc, beta, w, False))
+    out["gdn_fwd_channels_last"] = {"shape": list(x.shape), "bytes": 8 * n, "ms": t * 1e3, "gbs": 8 * n / t / 1e9}
+    xcr = xc.clone().requires_grad_(True)
+    yc = F.gdn(xcr, beta, w, False)
+    t = time_it(lambda: torch.autograd.grad(yc, (xcr, beta, w), gc, retain_graph=True))
+    out["gdn_bwd_channels_last"] = {"shape": list(x.shape), "bytes": 12 * n, "ms": t * 1e3, "gbs": 12 * n / t / 1e9}
+    del x, g, xr, y, xc, gc, xcr, yc
     # likelihood kernel: the step's latent is tiny (launch-latency bound); the roofline figure is quoted on the top of the
     # BASELINE cfg5 sweep (128x128x320 latent, batch 16 = 84M elements, 1 GB of traffic)
     for tag, shape in (("k1_fwd_step", (B, M, 16, 16)), ("k1_fwd_sweep_top", (16, 320, 128, 128))):
@@ -349,9 +357,13 @@ def kernel_rooflines(cfg, dev):
     for v in out.values():
         v["frac_of_hbm_peak"] = v["gbs"] / peak
     dom = out["gdn_bwd"]
-    roof = {"kernel": "gdn_bwd_kernel<GDN,vec> at the largest site of the step", "bound": "hbm", "achieved": dom["gbs"], "peak": peak,
-            "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"]}
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed ncu --set full capture
+    # (profiles/r01a_ncu_k1_gdn_first_version.txt: 1073.8 MB read + 498.1 MB written; the kernel's memory access pattern has
+    # not changed since).  Only meaningful for the cfg2 site shape.
+    traffic = 1.0737e9 + 0.4981e9 if (B, N) == (16, 128) else None
+    roof = {"kernel": "gdn_bwd_kernel (GDN backward) at the largest site of the step", "bound": "hbm", "achieved": dom["gbs"], "peak": peak,
+            "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01a_ncu_k1_gdn_first_version.txt",
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"]}
     return roof, out
 
 
