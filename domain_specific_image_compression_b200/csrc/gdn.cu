@@ -117,24 +117,30 @@ __global__ void __launch_bounds__(kThreads) gdn_fwd_nhwc_kernel(const float4 *__
                                                                 const float *__restrict__ gamma_weight, unsigned n4, int c4,
                                                                 float4 *__restrict__ y) {
     const Quad q = load_quad(bias_p, beta_param, gamma_weight, (int)(threadIdx.x % c4) * 4);
-    const unsigned stride = gridDim.x * blockDim.x * kUnroll;
-    for (unsigned v0 = blockIdx.x * (blockDim.x * kUnroll) + threadIdx.x; v0 < n4; v0 += stride) {
-        float4 a[kUnroll];
+    // a CTA walks CONTIGUOUS super-chunks of 2*kUnroll*blockDim float4 (32 KB at 256 threads): same DRAM-page friendly
+    // access as the NCHW kernel (the first NHWC version strode 4 KB apart inside one iteration: 83 % vs 97 % of peak)
+    const unsigned chunk = blockDim.x * kUnroll * 2;
+    for (unsigned base = blockIdx.x * chunk; base < n4; base += gridDim.x * chunk) {
 #pragma unroll
-        for (int k = 0; k < kUnroll; ++k) {
-            unsigned v = v0 + k * blockDim.x;
-            if (v < n4) a[k] = ldg_stream(x + v);
-        }
+        for (int half = 0; half < 2; ++half) {
+            const unsigned v0 = base + half * blockDim.x * kUnroll + threadIdx.x;
+            float4 a[kUnroll];
 #pragma unroll
-        for (int k = 0; k < kUnroll; ++k) {
-            unsigned v = v0 + k * blockDim.x;
-            if (v < n4) {
-                float4 o;
-                o.x = gdn1<INVERSE>(a[k].x, q.a[0], q.b[0], q.g[0]);
-                o.y = gdn1<INVERSE>(a[k].y, q.a[1], q.b[1], q.g[1]);
-                o.z = gdn1<INVERSE>(a[k].z, q.a[2], q.b[2], q.g[2]);
-                o.w = gdn1<INVERSE>(a[k].w, q.a[3], q.b[3], q.g[3]);
-                stg_stream(y + v, o);
+            for (int k = 0; k < kUnroll; ++k) {
+                unsigned v = v0 + k * blockDim.x;
+                if (v < n4) a[k] = ldg_stream(x + v);
+            }
+#pragma unroll
+            for (int k = 0; k < kUnroll; ++k) {
+                unsigned v = v0 + k * blockDim.x;
+                if (v < n4) {
+                    float4 o;
+                    o.x = gdn1<INVERSE>(a[k].x, q.a[0], q.b[0], q.g[0]);
+                    o.y = gdn1<INVERSE>(a[k].y, q.a[1], q.b[1], q.g[1]);
+                    o.z = gdn1<INVERSE>(a[k].z, q.a[2], q.b[2], q.g[2]);
+                    o.w = gdn1<INVERSE>(a[k].w, q.a[3], q.b[3], q.g[3]);
+                    stg_stream(y + v, o);
+                }
             }
         }
     }
@@ -254,25 +260,29 @@ __global__ void __launch_bounds__(kThreads) gdn_bwd_nhwc_kernel(const float4 *__
     const Quad q = load_quad(bias_p, beta_param, gamma_weight, cq * 4);
     float ab[4] = {0.f, 0.f, 0.f, 0.f}, ag[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
     constexpr int U = 2;
-    const unsigned stride = gridDim.x * blockDim.x * U;
-    for (unsigned v0 = blockIdx.x * (blockDim.x * U) + threadIdx.x; v0 < n4; v0 += stride) {
-        float4 xa[U], ga[U];
+    const unsigned chunk = blockDim.x * U * 4;   // contiguous super-chunk per CTA iteration (32 KB of x at 256 threads)
+    for (unsigned base = blockIdx.x * chunk; base < n4; base += gridDim.x * chunk) {
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            unsigned v = v0 + k * blockDim.x;
-            if (v < n4) { xa[k] = ldg_stream(x + v); ga[k] = ldg_stream(g + v); }
-        }
+        for (int part_i = 0; part_i < 4; ++part_i) {
+            const unsigned v0 = base + part_i * blockDim.x * U + threadIdx.x;
+            float4 xa[U], ga[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            unsigned v = v0 + k * blockDim.x;
-            if (v < n4) {
-                float4 o;
-                float hb, hg;
-                gdn_bwd1<INVERSE>(xa[k].x + q.a[0], ga[k].x, q.b[0], q.g[0], o.x, hb, hg); ab[0] += hb; ag[0] += hg; ax[0] += o.x;
-                gdn_bwd1<INVERSE>(xa[k].y + q.a[1], ga[k].y, q.b[1], q.g[1], o.y, hb, hg); ab[1] += hb; ag[1] += hg; ax[1] += o.y;
-                gdn_bwd1<INVERSE>(xa[k].z + q.a[2], ga[k].z, q.b[2], q.g[2], o.z, hb, hg); ab[2] += hb; ag[2] += hg; ax[2] += o.z;
-                gdn_bwd1<INVERSE>(xa[k].w + q.a[3], ga[k].w, q.b[3], q.g[3], o.w, hb, hg); ab[3] += hb; ag[3] += hg; ax[3] += o.w;
-                stg_stream(dx + v, o);
+            for (int k = 0; k < U; ++k) {
+                unsigned v = v0 + k * blockDim.x;
+                if (v < n4) { xa[k] = ldg_stream(x + v); ga[k] = ldg_stream(g + v); }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                unsigned v = v0 + k * blockDim.x;
+                if (v < n4) {
+                    float4 o;
+                    float hb, hg;
+                    gdn_bwd1<INVERSE>(xa[k].x + q.a[0], ga[k].x, q.b[0], q.g[0], o.x, hb, hg); ab[0] += hb; ag[0] += hg; ax[0] += o.x;
+                    gdn_bwd1<INVERSE>(xa[k].y + q.a[1], ga[k].y, q.b[1], q.g[1], o.y, hb, hg); ab[1] += hb; ag[1] += hg; ax[1] += o.y;
+                    gdn_bwd1<INVERSE>(xa[k].z + q.a[2], ga[k].z, q.b[2], q.g[2], o.z, hb, hg); ab[2] += hb; ag[2] += hg; ax[2] += o.z;
+                    gdn_bwd1<INVERSE>(xa[k].w + q.a[3], ga[k].w, q.b[3], q.g[3], o.w, hb, hg); ab[3] += hb; ag[3] += hg; ax[3] += o.w;
+                    stg_stream(dx + v, o);
+                }
             }
         }
     }
@@ -355,8 +365,8 @@ extern "C" int sic_gdn_fwd(const float *x, const float *bias, const float *beta_
     } else if (channels_last && C % 4 == 0 && C <= 4 * kThreads && al) {
         unsigned n4 = (unsigned)(n / 4);
         const int c4 = C / 4, threads = nhwc_threads(C);
-        long want = ((long)n4 + threads * kUnroll - 1) / (threads * kUnroll);
-        unsigned grid = (unsigned)(want < (long)sms * 8 ? want : (long)sms * 8);
+        long want = ((long)n4 + threads * kUnroll * 2 - 1) / (threads * kUnroll * 2);
+        unsigned grid = (unsigned)(want < (long)sms * 32 ? want : (long)sms * 32);
         if (inverse) gdn_fwd_nhwc_kernel<true><<<grid, threads, 0, st>>>((const float4 *)x, bias, beta_param, gamma_weight, n4, c4, (float4 *)y);
         else gdn_fwd_nhwc_kernel<false><<<grid, threads, 0, st>>>((const float4 *)x, bias, beta_param, gamma_weight, n4, c4, (float4 *)y);
     } else {
@@ -395,7 +405,7 @@ extern "C" int sic_gdn_bwd(const float *x, const float *bias, const float *g, co
         }
         const int threads = nhwc_threads(C);
         const unsigned n4 = (unsigned)(n / 4);
-        long want = ((long)n4 + threads * 2 - 1) / (threads * 2);
+        long want = ((long)n4 + threads * 8 - 1) / (threads * 8);
         const unsigned grid = (unsigned)(want < nhwc_bwd_grid() ? want : nhwc_bwd_grid());
         const size_t smem = (size_t)threads * 12 * sizeof(float);
         if (inverse) gdn_bwd_nhwc_kernel<true><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, (float4 *)dx, part);
