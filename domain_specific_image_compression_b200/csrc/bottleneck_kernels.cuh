@@ -52,6 +52,7 @@ constexpr int kMaxPanels = 48;
 struct TConst {
     float inv_sigma, inv_nu, A, B2;  // nll = A + B2 * log2(1 + (x*inv_sigma)^2 * inv_nu),  B2 = (nu+1)/2
     float nu, lc2, kstep;            // cdf_diff: log2 of the unit-scale normaliser, quadrature panel scale
+    float rn, inv_rn, inv_ds;        // cdf_diff forward: sqrt(nu), 1/sqrt(nu), panels per unit of asinh(t/sqrt(nu))
 };
 __device__ __forceinline__ TConst t_const(float sigma_raw, float nu_raw) {
     float s = clamp_keep_nan(sigma_raw, kSigmaMin, kSigmaMax);  // distributions.py:23
@@ -66,6 +67,9 @@ __device__ __forceinline__ TConst t_const(float sigma_raw, float nu_raw) {
     c.nu = n;
     c.lc2 = -c.A + __log2f(s);         // log2 Gamma((nu+1)/2) / (sqrt(nu pi) Gamma(nu/2))
     c.kstep = kPanel * rsqrtf(n + 1.0f);
+    c.inv_rn = rsqrtf(n);
+    c.rn = n * c.inv_rn;
+    c.inv_ds = (n + 1.0f) * rsqrtf(n + 1.0f) * (1.0f / kPanel);
     return c;
 }
 // One MUFU.LG2 per element.  Error budget in bits: B2 * (2^-24 rounding of 1+u  +  2^-22 MUFU) * log2e-ish <= 1.7e-5 at the
@@ -149,6 +153,95 @@ __device__ __forceinline__ float t_cdf_nll(float x, const TConst &c) {
     return -(c.lc2 + eref + __log2f(S));
 }
 
+
+// ---- warp-cooperative forward --------------------------------------------------------------------------------------------
+// The per-lane panel loop above leaves 20 of 32 lanes idle on average (ncu r01: 12.0 active threads per instruction): elements
+// near zero with a small sigma need 4+ panels, their neighbours one.  Here the panels of the 32 elements a warp holds are
+// pooled and dealt out 32 at a time.  That needs panel boundaries any lane can compute, so they are uniform in
+// s = asinh(t / sqrt(nu)) — the closed form of the marching rule (dt/ds = sqrt(nu + t^2)); calibrated in float64 against
+// scipy like the marching rule: worst relative error 2.8e-7 at 1.5/sqrt(nu+1) per panel.
+template <bool UNIFORM>
+__device__ __forceinline__ float warp_cdf_nll(float x, bool active, const TConst &c) {
+    __shared__ float s_part[kWarpsPerCta][32];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    float *part = s_part[threadIdx.x >> 5];
+    const float lo = (x - 0.5f) * c.inv_sigma, hi = (x + 0.5f) * c.inv_sigma;
+    const bool one_sided = lo >= 0.f || hi <= 0.f;
+    // piece 0: [A0, B0] (one-sided bin, or the right half of a straddling bin); piece 1: [0, B1] (left half, mirrored)
+    const float A0 = one_sided ? (lo >= 0.f ? lo : -hi) : 0.f;
+    const float B0 = one_sided ? (lo >= 0.f ? hi : -lo) : hi;
+    const float B1 = one_sided ? 0.f : -lo;
+    const float eref = one_sided ? -c.B2 * __log2f(fmaf(A0 * A0, c.inv_nu, 1.0f)) : 0.f;
+    auto asinh_f = [](float u) { return __logf(u + sqrtf(fmaf(u, u, 1.0f))); };
+    const float sA0 = asinh_f(A0 * c.inv_rn), sB0 = asinh_f(B0 * c.inv_rn), sB1 = asinh_f(B1 * c.inv_rn);
+    int n0 = (int)fminf(fmaxf(ceilf((sB0 - sA0) * c.inv_ds), 1.0f), (float)kMaxPanels);
+    int n1 = one_sided ? 0 : (int)fminf(fmaxf(ceilf(sB1 * c.inv_ds), 1.0f), (float)kMaxPanels);
+    if (!active) { n0 = 0; n1 = 0; }
+    const float d0 = (sB0 - sA0) / (float)max(n0, 1), d1 = sB1 / (float)max(n1, 1);
+    const int T = n0 + n1;
+    int incl = T;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(full, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int excl = incl - T;
+    const int total = __shfl_sync(full, incl, 31);
+    float S = 0.f;
+    for (int base = 0; base < total; base += 32) {
+        const int j = base + lane;
+        int own = 0;  // largest lane whose exclusive offset is <= j (lanes without panels share their successor's offset)
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            int cand = own + step;
+            int ev = __shfl_sync(full, excl, cand & 31);
+            if (cand < 32 && ev <= j) own = cand;
+        }
+        const int k = j - __shfl_sync(full, excl, own);
+        const int on0 = __shfl_sync(full, n0, own), on1 = __shfl_sync(full, n1, own);
+        const float oA0 = __shfl_sync(full, A0, own), osA0 = __shfl_sync(full, sA0, own), oB0 = __shfl_sync(full, B0, own);
+        const float od0 = __shfl_sync(full, d0, own), oB1 = __shfl_sync(full, B1, own), od1 = __shfl_sync(full, d1, own);
+        const float oeref = __shfl_sync(full, eref, own);
+        float inv_nu = c.inv_nu, B2 = c.B2, rn = c.rn;
+        if (!UNIFORM) {
+            inv_nu = __shfl_sync(full, c.inv_nu, own);
+            B2 = __shfl_sync(full, c.B2, own);
+            rn = __shfl_sync(full, c.rn, own);
+        }
+        float I = 0.f;
+        if (j < total) {
+            const bool second = k >= on0;
+            const int kk = second ? k - on0 : k, np = second ? on1 : on0;
+            const float A = second ? 0.f : oA0, sA = second ? 0.f : osA0, B = second ? oB1 : oB0, d = second ? od1 : od0;
+            auto bound = [&](int idx) {   // exact ends, closed form inside: the same expression for both neighbours of a boundary
+                if (idx == 0) return A;
+                if (idx == np) return B;
+                float e = __expf(fmaf((float)idx, d, sA));
+                return rn * 0.5f * (e - __fdividef(1.0f, e));
+            };
+            const float t0 = bound(kk), t1 = bound(kk + 1);
+            const float m = 0.5f * (t0 + t1), h = 0.5f * (t1 - t0);
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int sgn = -1; sgn <= 1; sgn += 2) {
+                    float l2, w;
+                    acc = fmaf(kGLw[i], t_fs(fmaf(h, sgn * kGLx[i], m), inv_nu, B2, oeref, l2, w), acc);
+                }
+            }
+            I = h * acc;
+        }
+        part[lane] = I;
+        __syncwarp();
+        const int j_begin = max(excl, base), j_end = min(incl, base + 32);   // my own panels inside this deal, in order
+        for (int jj = j_begin; jj < j_end; ++jj) S += part[jj - base];
+        __syncwarp();
+    }
+    return active ? -(c.lc2 + eref + __log2f(S)) : 0.f;
+}
+
 struct GConst {
     float A, Bc;  // nll = A + Bc * x^2
 };
@@ -167,12 +260,14 @@ __device__ __forceinline__ float quantize1(float y, int quant_mode, float noise)
     return y;
 }
 
+// `active`: whether this lane holds a real element.  The cdf_diff modes are warp-cooperative, so every lane of the warp must
+// make the call (inactive lanes contribute no panels); the other modes ignore the flag.
 template <int MODE>
-__device__ __forceinline__ float elem_nll(float x, const TConst &tc, const GConst &gc, float sg, float nu) {
+__device__ __forceinline__ float elem_nll(float x, bool active, const TConst &tc, const GConst &gc, float sg, float nu) {
     if (MODE == MODE_GAUSS) return fmaf(gc.Bc, x * x, gc.A);
     if (MODE == MODE_T_SPATIAL) return t_nll(x, t_const(sg, nu));
-    if (MODE == MODE_CDF_SPATIAL) return t_cdf_nll(x, t_const(sg, nu));
-    if (MODE == MODE_CDF_BCAST) return t_cdf_nll(x, tc);
+    if (MODE == MODE_CDF_SPATIAL) return warp_cdf_nll<false>(x, active, t_const(active ? sg : 1.0f, active ? nu : 4.0f));
+    if (MODE == MODE_CDF_BCAST) return warp_cdf_nll<true>(x, active, tc);
     return t_nll(x, tc);
 }
 
@@ -202,7 +297,7 @@ __device__ __forceinline__ bool retire_and_check_last(unsigned int *ticket) {
 // QUANT and HAS_MU are compile-time so that the prefetch registers of unused optional inputs (noise tensor, mu map)
 // disappear: the common training instance (broadcast, Philox, no mu) must stay <= 64 registers for 4 CTAs per SM.
 template <int MODE, bool VEC, int QUANT, bool HAS_MU>
-__global__ void __launch_bounds__(kThreads, 4) bottleneck_fwd_kernel(
+__global__ void __launch_bounds__(kThreads, is_cdf(MODE) ? 2 : 4) bottleneck_fwd_kernel(
     const float *__restrict__ y, const float *__restrict__ noise, uint64_t *__restrict__ philox,
     const float *__restrict__ mu_in, const float *__restrict__ sigma, const float *__restrict__ nu, Shape sh,
     int mu_layout, float *__restrict__ y_tilde, float *__restrict__ nll, float *__restrict__ bits, float *__restrict__ psum,
@@ -235,7 +330,8 @@ __global__ void __launch_bounds__(kThreads, 4) bottleneck_fwd_kernel(
             constexpr int U = is_spatial(MODE) ? 2 : 4;  // vectors in flight per lane (spatial mode streams 3 tensors)
             const int v0 = e0 >> 2, v1 = e1 >> 2;
             const long vbase = base >> 2;
-            for (int v = v0 + lane; v < v1; v += 32 * U) {
+            for (int vb = v0; vb < v1; vb += 32 * U) {   // warp-uniform trip count (the cdf_diff modes are warp-cooperative)
+                const int v = vb + lane;
                 float4 yy[U], nn[U], ss[U], uu[U], mm[U];
 #pragma unroll
                 for (int k = 0; k < U; ++k) {
@@ -253,23 +349,26 @@ __global__ void __launch_bounds__(kThreads, 4) bottleneck_fwd_kernel(
                 }
 #pragma unroll
                 for (int k = 0; k < U; ++k) {
-                    int vv = v + 32 * k;
-                    if (vv < v1) {
-                        long gi = vbase + vv;
+                    const int vv = v + 32 * k;
+                    const bool ok = vv < v1;
+                    const long gi = vbase + vv;
+                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f), l, m4 = make_float4(mu_row, mu_row, mu_row, mu_row);
+                    if (ok) {
                         if (quant_mode == SIC_QUANT_NOISE_PHILOX) {
                             uint4 r = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)((uint64_t)gi >> 32), off.x, off.y), key);
                             nn[k] = make_float4(u32_to_noise(r.x), u32_to_noise(r.y), u32_to_noise(r.z), u32_to_noise(r.w));
                         }
-                        float4 q, l;
-                        float4 m4 = (mu != nullptr && mu_layout == SIC_PARAM_SPATIAL) ? mm[k] : make_float4(mu_row, mu_row, mu_row, mu_row);
+                        if (mu != nullptr && mu_layout == SIC_PARAM_SPATIAL) m4 = mm[k];
                         q.x = quantize1(yy[k].x, quant_mode, nn[k].x);
                         q.y = quantize1(yy[k].y, quant_mode, nn[k].y);
                         q.z = quantize1(yy[k].z, quant_mode, nn[k].z);
                         q.w = quantize1(yy[k].w, quant_mode, nn[k].w);
-                        l.x = elem_nll<MODE>(q.x - m4.x, tc, gc, ss[k].x, uu[k].x);
-                        l.y = elem_nll<MODE>(q.y - m4.y, tc, gc, ss[k].y, uu[k].y);
-                        l.z = elem_nll<MODE>(q.z - m4.z, tc, gc, ss[k].z, uu[k].z);
-                        l.w = elem_nll<MODE>(q.w - m4.w, tc, gc, ss[k].w, uu[k].w);
+                    }
+                    l.x = elem_nll<MODE>(q.x - m4.x, ok, tc, gc, ss[k].x, uu[k].x);
+                    l.y = elem_nll<MODE>(q.y - m4.y, ok, tc, gc, ss[k].y, uu[k].y);
+                    l.z = elem_nll<MODE>(q.z - m4.z, ok, tc, gc, ss[k].z, uu[k].z);
+                    l.w = elem_nll<MODE>(q.w - m4.w, ok, tc, gc, ss[k].w, uu[k].w);
+                    if (ok) {
                         if (y_tilde != nullptr) stg_stream(reinterpret_cast<float4 *>(y_tilde) + gi, q);
                         if (nll != nullptr) stg_stream(reinterpret_cast<float4 *>(nll) + gi, l);
                         acc += (l.x + l.y) + (l.z + l.w);
@@ -277,24 +376,30 @@ __global__ void __launch_bounds__(kThreads, 4) bottleneck_fwd_kernel(
                 }
             }
         } else {
-            for (int e = e0 + lane; e < e1; e += 32) {
-                long gi = base + e;
-                float n1 = 0.0f;
-                if (quant_mode == SIC_QUANT_NOISE_TENSOR) n1 = noise[gi];
-                if (quant_mode == SIC_QUANT_NOISE_PHILOX) {
-                    long v = gi >> 2;
-                    uint4 r = philox4x32_10(make_uint4((uint32_t)v, (uint32_t)((uint64_t)v >> 32), off.x, off.y), key);
-                    int j = (int)(gi & 3);
-                    n1 = u32_to_noise(j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w);
+            for (int eb = e0; eb < e1; eb += 32) {   // warp-uniform trip count
+                const int e = eb + lane;
+                const bool ok = e < e1;
+                const long gi = base + e;
+                float q = 0.f, m1 = mu_row, sg = 0.f, nv = 0.f;
+                if (ok) {
+                    float n1 = 0.0f;
+                    if (quant_mode == SIC_QUANT_NOISE_TENSOR) n1 = noise[gi];
+                    if (quant_mode == SIC_QUANT_NOISE_PHILOX) {
+                        long v = gi >> 2;
+                        uint4 r = philox4x32_10(make_uint4((uint32_t)v, (uint32_t)((uint64_t)v >> 32), off.x, off.y), key);
+                        int j = (int)(gi & 3);
+                        n1 = u32_to_noise(j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w);
+                    }
+                    q = quantize1(y[gi], quant_mode, n1);
+                    if (mu != nullptr && mu_layout == SIC_PARAM_SPATIAL) m1 = mu[gi];
+                    if (is_spatial(MODE)) { sg = sigma[gi]; nv = nu[gi]; }
                 }
-                float q = quantize1(y[gi], quant_mode, n1);
-                float m1 = (mu != nullptr && mu_layout == SIC_PARAM_SPATIAL) ? mu[gi] : mu_row;
-                float sg = 0.f, nv = 0.f;
-                if (is_spatial(MODE)) { sg = sigma[gi]; nv = nu[gi]; }
-                float l = elem_nll<MODE>(q - m1, tc, gc, sg, nv);
-                if (y_tilde != nullptr) y_tilde[gi] = q;
-                if (nll != nullptr) nll[gi] = l;
-                acc += l;
+                float l = elem_nll<MODE>(q - m1, ok, tc, gc, sg, nv);
+                if (ok) {
+                    if (y_tilde != nullptr) y_tilde[gi] = q;
+                    if (nll != nullptr) nll[gi] = l;
+                    acc += l;
+                }
             }
         }
         acc = warp_sum(acc);
