@@ -67,6 +67,9 @@ def _workspace(device: torch.device, nbytes: int, kind: str = "ticketed") -> tor
 def philox_state(device: torch.device) -> torch.Tensor:
     """Device-resident {seed, offset} for the in-kernel noise; re-seeded whenever torch.manual_seed changes."""
     seed = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        # data-parallel ranks share torch's seed; give every rank its own noise stream (rank 0 keeps the plain seed)
+        seed = (seed + 0x9E3779B97F4A7C15 * torch.distributed.get_rank()) & 0x7FFFFFFFFFFFFFFF
     st = _philox.get(device.index)
     if st is None or st[0] != seed:
         t = torch.tensor([seed, 0], dtype=torch.int64, device=device)
@@ -152,6 +155,10 @@ def bottleneck(y: torch.Tensor, sigma: torch.Tensor, nu: Optional[torch.Tensor] 
     uniform draw (parity mode) instead of the in-kernel Philox generator."""
     if quant not in _QUANT:
         raise ValueError(f"Unknown quant mode: {quant}")            # model.py:35
+    if y.numel() == 0:                                               # empty batch / empty latent: nothing to launch
+        _require_cuda_f32(y, "y")
+        z = torch.zeros(y.shape[0], dtype=torch.float32, device=y.device)
+        return y, (torch.empty_like(y) if want_nll else None), z + 0.0 * y.sum()
     q = _QUANT[quant]
     if quant == "noise" and noise is not None:
         q = QUANT_NOISE_TENSOR
@@ -224,6 +231,9 @@ def gdn(x: torch.Tensor, beta_param: torch.Tensor, gamma_weight: torch.Tensor, i
         bias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Diagonal GDN/IGDN (K2), bit-exact with layers.py:19-27 on the same device arithmetic.  `bias`: the producing
     convolution's bias, folded in as GDN(x + bias) (same rounding as PyTorch's conv -> add_(bias) -> GDN)."""
+    if x.numel() == 0:
+        _require_cuda_f32(x, "x")
+        return x + 0.0 * (beta_param.sum() + gamma_weight.sum())     # empty in, empty out (keeps the autograd graph connected)
     return _GDN.apply(x, beta_param, gamma_weight, inverse, bias)
 
 

@@ -321,3 +321,16 @@ def test_cdfdiff_model_mode_trains(golden):
         if lik == "cdf_diff":
             assert float(out["nll_y"].min()) >= 0.0
     assert abs(rates["cdf_diff"] - rates["density"]) < 0.25 * rates["density"]
+
+
+def test_empty_inputs():
+    """Empty batch / empty latent: the reference's op chains return empty tensors; so do we (no launch)."""
+    F = _F()
+    y = torch.zeros(0, 8, 4, 4, device="cuda")
+    yt, nll, bits = F.bottleneck(y, torch.ones(0, 8, 1, 1, device="cuda"), torch.ones(0, 8, 1, 1, device="cuda"), quant="round")
+    assert yt.shape == y.shape and nll.shape == y.shape and bits.shape == (0,)
+    y = torch.zeros(2, 8, 0, 4, device="cuda")
+    yt, nll, bits = F.bottleneck(y, torch.ones(2, 8, 1, 1, device="cuda"), torch.full((2, 8, 1, 1), 3.0, device="cuda"), quant="noise")
+    assert nll.numel() == 0 and bits.tolist() == [0.0, 0.0]
+    x = torch.zeros(0, 16, 8, 8, device="cuda")
+    assert F.gdn(x, torch.ones(16, device="cuda"), torch.ones(16, 1, 1, 1, device="cuda")).shape == x.shape
