@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsic.so")
 QUANT_NONE, QUANT_ROUND, QUANT_NOISE_TENSOR, QUANT_NOISE_PHILOX = 0, 1, 2, 3
 LIK_STUDENTT_DENSITY, LIK_GAUSSIAN, LIK_STUDENTT_CDFDIFF = 0, 1, 2
 PARAM_BROADCAST, PARAM_SPATIAL, PARAM_CHANNEL = 0, 1, 2
+DENSE_SERIAL, DENSE_PIPELINED = 0, 1
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -32,6 +33,7 @@ PROTOTYPES = {
     "sic_gdn_bwd_workspace_bytes": (_z, [_i, _i, _i]),
     "sic_gdn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "sic_gdn_dense_fwd": (_i, [_p, _p, _p, _l, _i, _i, _p, _p]),
+    "sic_gdn_dense_fwd_variant": (_i, [_p, _p, _p, _l, _i, _i, _p, _i, _p]),
     "sic_ssim_tiles": (_l, [_i, _i]),
     "sic_ssim_fwd": (_i, [_p, _p, _i, _i, _i, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p]),
     "sic_ssim_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),

@@ -28,6 +28,7 @@ SOURCES = [
     ("bottleneck_cdf.cu", []),
     ("gdn.cu", []),
     ("gdn_dense.cu", []),
+    ("gdn_dense_ws.cu", []),
     ("msssim.cu", []),
     ("tables.cu", ["-fmad=false"]),
     ("rans_host.cpp", []),

@@ -246,15 +246,16 @@ int launch_dense(const float *x, const float *beta_param, const float *gamma_par
 }  // namespace
 }  // namespace sic
 
+namespace sic {
+// gdn_dense_ws.cu: the warp-specialised, pipelined kernel (SIC_DENSE_PIPELINED)
+int gdn_dense_ws_dispatch(const float *x, const float *beta_param, const float *gamma_param, long positions, int C, int inverse,
+                          float *y, cudaStream_t st);
+}  // namespace sic
+
 using namespace sic;
 
-extern "C" int sic_gdn_dense_fwd(const float *x, const float *beta_param, const float *gamma_param, long positions, int C,
-                                 int inverse, float *y, void *stream) {
-    SIC_CHECK_ARG(positions > 0 && C > 0, "sic_gdn_dense_fwd: empty shape positions=%ld C=%d", positions, C);
-    SIC_CHECK_ARG(x && y && beta_param && gamma_param, "sic_gdn_dense_fwd: null pointer");
-    SIC_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)gamma_param & 15) == 0,
-                  "sic_gdn_dense_fwd: tensors must be 16-byte aligned");
-    cudaStream_t st = (cudaStream_t)stream;
+static int dense_serial_dispatch(const float *x, const float *beta_param, const float *gamma_param, long positions, int C,
+                                 int inverse, float *y, cudaStream_t st) {
     switch (C) {
         case 32: return launch_dense<32>(x, beta_param, gamma_param, positions, inverse, y, st);
         case 64: return launch_dense<64>(x, beta_param, gamma_param, positions, inverse, y, st);
@@ -265,4 +266,21 @@ extern "C" int sic_gdn_dense_fwd(const float *x, const float *beta_param, const 
                       "memory: C in {32,64,96,128}; wider layers need K-streaming)", C);
             return SIC_E_UNSUPPORTED;
     }
+}
+
+extern "C" int sic_gdn_dense_fwd_variant(const float *x, const float *beta_param, const float *gamma_param, long positions, int C,
+                                         int inverse, float *y, int variant, void *stream) {
+    SIC_CHECK_ARG(positions > 0 && C > 0, "sic_gdn_dense_fwd: empty shape positions=%ld C=%d", positions, C);
+    SIC_CHECK_ARG(x && y && beta_param && gamma_param, "sic_gdn_dense_fwd: null pointer");
+    SIC_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)gamma_param & 15) == 0,
+                  "sic_gdn_dense_fwd: tensors must be 16-byte aligned");
+    SIC_CHECK_ARG(variant == SIC_DENSE_SERIAL || variant == SIC_DENSE_PIPELINED, "sic_gdn_dense_fwd: unknown variant %d", variant);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (variant == SIC_DENSE_PIPELINED) return gdn_dense_ws_dispatch(x, beta_param, gamma_param, positions, C, inverse, y, st);
+    return dense_serial_dispatch(x, beta_param, gamma_param, positions, C, inverse, y, st);
+}
+
+extern "C" int sic_gdn_dense_fwd(const float *x, const float *beta_param, const float *gamma_param, long positions, int C,
+                                 int inverse, float *y, void *stream) {
+    return sic_gdn_dense_fwd_variant(x, beta_param, gamma_param, positions, C, inverse, y, SIC_DENSE_DEFAULT, stream);
 }

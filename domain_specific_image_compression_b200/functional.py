@@ -242,7 +242,7 @@ class _GDNDense(torch.autograd.Function):
     (plain library GEMMs, cuBLAS) on the re-parameterised gamma — the dense path is a capability the reference never runs."""
 
     @staticmethod
-    def forward(ctx, x, beta_param, gamma_param, inverse: bool):
+    def forward(ctx, x, beta_param, gamma_param, inverse: bool, variant=None):
         lib = _lib.load()
         if x.dim() != 4:
             raise _lib.SicError("dense GDN expects [B,C,H,W]")
@@ -254,8 +254,12 @@ class _GDNDense(torch.autograd.Function):
             raise _lib.SicError(f"dense GDN parameters {tuple(beta_param.shape)}/{tuple(gamma_param.shape)} do not match C={C}")
         y = torch.empty_like(xc)
         with torch.cuda.device(x.device):
-            _launch(lib.sic_gdn_dense_fwd(_ptr(xc), _ptr(beta_param), _ptr(gamma_param), B * H * W, C, int(inverse), _ptr(y),
-                                          _stream()), "sic_gdn_dense_fwd")
+            if variant is None:
+                rc = lib.sic_gdn_dense_fwd(_ptr(xc), _ptr(beta_param), _ptr(gamma_param), B * H * W, C, int(inverse), _ptr(y), _stream())
+            else:
+                rc = lib.sic_gdn_dense_fwd_variant(_ptr(xc), _ptr(beta_param), _ptr(gamma_param), B * H * W, C, int(inverse), _ptr(y),
+                                                   int(variant), _stream())
+            _launch(rc, "sic_gdn_dense_fwd")
         ctx.save_for_backward(xc, beta_param, gamma_param)
         ctx.inverse = bool(inverse)
         return y
@@ -281,12 +285,14 @@ class _GDNDense(torch.autograd.Function):
         dgamma = h.t() @ X2                                          # dgamma_ij = sum_p h_i x2_j
         dbeta = h.sum(0)
         dx = dX.reshape(B, H, W, C).permute(0, 3, 1, 2)
-        return dx, dbeta * 2.0 * beta_param, dgamma * 2.0 * gamma_param, None
+        return dx, dbeta * 2.0 * beta_param, dgamma * 2.0 * gamma_param, None, None
 
 
-def gdn_dense(x: torch.Tensor, beta_param: torch.Tensor, gamma_param: torch.Tensor, inverse: bool = False) -> torch.Tensor:
-    """Dense-gamma GDN/IGDN on tcgen05 tensor cores (G3); returns a channels_last tensor."""
-    return _GDNDense.apply(x, beta_param, gamma_param, inverse)
+def gdn_dense(x: torch.Tensor, beta_param: torch.Tensor, gamma_param: torch.Tensor, inverse: bool = False,
+              variant=None) -> torch.Tensor:
+    """Dense-gamma GDN/IGDN on tcgen05 tensor cores (G3); returns a channels_last tensor.
+    variant: None = the library default, _lib.DENSE_SERIAL or _lib.DENSE_PIPELINED to pick the kernel (include/sic.h)."""
+    return _GDNDense.apply(x, beta_param, gamma_param, inverse, variant)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -103,6 +103,14 @@ int sic_gdn_bwd(const float *x, const float *bias, const float *g, const float *
  *   This build: C in {32, 64, 96, 128} (operands resident in shared memory), otherwise SIC_E_UNSUPPORTED. */
 int sic_gdn_dense_fwd(const float *x, const float *beta_param, const float *gamma_param, long positions, int C, int inverse,
                       float *y, void *stream);
+/* The same operation with the kernel chosen explicitly (both are kept so each can be parity-tested and timed):
+ *   SIC_DENSE_SERIAL     one CTA per SM walks load -> square -> MMA -> epilogue tile by tile (csrc/gdn_dense.cu);
+ *   SIC_DENSE_PIPELINED  warp-specialised producer / MMA / epilogue roles over mbarrier pipelines, two TMEM accumulator
+ *                        stages, gamma as the A operand so the epilogue needs no transpose (csrc/gdn_dense_ws.cu).
+ * sic_gdn_dense_fwd uses SIC_DENSE_DEFAULT. */
+enum { SIC_DENSE_SERIAL = 0, SIC_DENSE_PIPELINED = 1, SIC_DENSE_DEFAULT = SIC_DENSE_PIPELINED };
+int sic_gdn_dense_fwd_variant(const float *x, const float *beta_param, const float *gamma_param, long positions, int C,
+                              int inverse, float *y, int variant, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * K4  symbols: eval_selfcontained_entropy.py:39-40,48 / :52-53,62 (per patch, no host sync).

@@ -87,11 +87,16 @@ if args.only in ("", "dense"):
         beta = torch.sqrt(torch.rand(N, device=dev) + 0.5)
         gm = torch.sqrt(torch.rand(N, N, device=dev) * 0.02 + torch.eye(N, device=dev) * 0.1 + 2.0 ** -18)
         n = x.numel()
-        for inv in (False, True):
-            t = time_it(lambda: F.gdn_dense(x, beta, gm, inv))
-            report(f"{'igdn' if inv else 'gdn'}_dense_fwd tcgen05 nhwc", x.shape, 8 * n, t)
-            rows[-1]["tflops_tf32_2pass"] = 2 * 2 * N * N * (n // N) / t / 1e12
-            print(f"    -> {rows[-1]['tflops_tf32_2pass']:.1f} TFLOP/s of tf32 MMA work (hi+lo passes)")
+        for variant, vname in ((0, "serial"), (1, "pipelined")):
+            for inv in (False, True):
+                try:
+                    t = time_it(lambda: F.gdn_dense(x, beta, gm, inv, variant))
+                except Exception as e:   # keep the sweep going if one variant is broken on this box
+                    print(f"dense {vname} inv={inv}: FAILED {e}", flush=True)
+                    continue
+                report(f"{'igdn' if inv else 'gdn'}_dense_fwd tcgen05 nhwc {vname}", x.shape, 8 * n, t)
+                rows[-1]["tflops_tf32_2pass"] = 2 * 2 * N * N * (n // N) / t / 1e12
+                print(f"    -> {rows[-1]['tflops_tf32_2pass']:.1f} TFLOP/s of tf32 MMA work (hi+lo passes)")
         del x
 if args.json:
     json.dump({"peak_gbs": PEAK, "rows": rows}, open(args.json, "w"), indent=1)

@@ -160,9 +160,14 @@ def _tf32_trunc(a):
     return (a.astype(np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
 
 
+DENSE_VARIANTS = [0, 1]      # include/sic.h: SIC_DENSE_SERIAL, SIC_DENSE_PIPELINED
+
+
+@pytest.mark.parametrize("variant", DENSE_VARIANTS)
 @pytest.mark.parametrize("inverse", [False, True])
-@pytest.mark.parametrize("shape", [(2, 128, 16, 24), (1, 64, 9, 7), (3, 32, 5, 5), (2, 96, 12, 12), (1, 128, 1, 3)])
-def test_dense_gdn_forward_vs_oracle(shape, inverse):
+@pytest.mark.parametrize("shape", [(2, 128, 16, 24), (1, 64, 9, 7), (3, 32, 5, 5), (2, 96, 12, 12), (1, 128, 1, 3),
+                                   (1, 128, 10, 20), (1, 96, 7, 13)])
+def test_dense_gdn_forward_vs_oracle(shape, inverse, variant):
     """tcgen05 kernel vs the float64 oracle (F.conv2d(x^2, gamma, beta) semantics).  gamma is consumed at TF32 precision,
     so the tight comparison uses the oracle with gamma truncated to TF32; against the untruncated oracle the difference is
     the documented 2^-11 parameter perturbation."""
@@ -172,7 +177,7 @@ def test_dense_gdn_forward_vs_oracle(shape, inverse):
     x = (rng.standard_normal(shape) * 2).astype(np.float32)
     beta_p = np.sqrt(rng.random(C) + 0.5).astype(np.float32)
     gamma_p = np.sqrt(rng.random((C, C)) * 0.02 + np.eye(C) * 0.1 + 2.0 ** -18).astype(np.float32)
-    y = F.gdn_dense(dev(x), dev(beta_p), dev(gamma_p), inverse)
+    y = F.gdn_dense(dev(x), dev(beta_p), dev(gamma_p), inverse, variant)
     assert y.shape == tuple(shape) and y.is_contiguous(memory_format=torch.channels_last) or min(H, W) == 1 or C == 1
     beta = (beta_p * beta_p - np.float32(2.0 ** -18)).astype(np.float32)
     gamma = (gamma_p * gamma_p - np.float32(2.0 ** -18)).astype(np.float32)
@@ -181,6 +186,30 @@ def test_dense_gdn_forward_vs_oracle(shape, inverse):
     got = y.cpu().numpy().astype(np.float64)
     assert np.abs(got - ref_t).max() <= 5e-6 * np.abs(ref_t).max() + 1e-7
     assert np.abs(got - ref).max() <= 1e-3 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("variant", DENSE_VARIANTS)
+@pytest.mark.parametrize("C,positions", [(128, 148 * 128 * 3 + 77), (64, 148 * 128 * 5 + 64), (96, 148 * 128 * 2 + 1)])
+def test_dense_gdn_many_tiles_per_cta(C, positions, variant):
+    """More tiles than 2 x SMs: every persistent CTA wraps its shared-memory stage and both TMEM accumulator stages several
+    times (the pipelined kernel's mbarrier phases), and the last tile is ragged.  The two kernels must also agree with each
+    other to rounding (same hi/lo products, different summation engines only in the epilogue's rsqrt)."""
+    F = _F()
+    rng = np.random.default_rng(C + positions)
+    x = (rng.standard_normal((1, C, positions, 1)) * 2).astype(np.float32)
+    beta_p = np.sqrt(rng.random(C) + 0.5).astype(np.float32)
+    gamma_p = np.sqrt(rng.random((C, C)) * 0.02 + np.eye(C) * 0.1 + 2.0 ** -18).astype(np.float32)
+    y = F.gdn_dense(dev(x), dev(beta_p), dev(gamma_p), False, variant)
+    beta = (beta_p * beta_p - np.float32(2.0 ** -18)).astype(np.float32)
+    gamma = (gamma_p * gamma_p - np.float32(2.0 ** -18)).astype(np.float32)
+    ref_t = R.gdn_dense_fwd_f64(x, beta, _tf32_trunc(gamma), False)
+    got = y.cpu().numpy().astype(np.float64)
+    assert got.shape == ref_t.shape
+    err = np.abs(got - ref_t)
+    assert err.max() <= 5e-6 * np.abs(ref_t).max() + 1e-7, f"worst position {np.unravel_index(err.argmax(), err.shape)}"
+    # idempotent across back-to-back launches on the same stream (no state leaks between launches)
+    y2 = F.gdn_dense(dev(x), dev(beta_p), dev(gamma_p), False, variant)
+    assert torch.equal(y, y2)
 
 
 def test_dense_gdn_equals_diag_path_for_diagonal_gamma():
