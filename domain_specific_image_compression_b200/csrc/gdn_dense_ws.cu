@@ -5,20 +5,24 @@
 // gdn_dense.cu runs load -> square -> MMA -> epilogue strictly one after the other on every tile (48 % of the HBM peak).  Here
 // the three phases of consecutive tiles overlap:
 //
-//   producer warps (8)   x tile (128 positions x C, one contiguous block of channels-last memory) -> registers (requested one
+//   producer warps (8)   x tile (TN positions x C, one contiguous block of channels-last memory) -> registers (requested one
 //                        tile ahead) -> x^2 split exactly into tf32 hi + lo -> shared memory in the K-major SWIZZLE_128B UMMA
 //                        layout -> mbarrier full[s]
 //   MMA warp (1 thread)  D[c_out, pos] (TMEM, 2 accumulator stages) = G[c_out, c_in] (smem, resident) * X2[pos, c_in]^T,
-//                        2 * C/8 tcgen05.mma kind::tf32 of shape 128 x 128 x 8; tcgen05.commit -> empty[s] and tmem_full[a]
-//   epilogue warps (8)   tcgen05.ld: lane = output channel, columns = positions.  With channels-last activations the 32 lanes of a
-//                        warp therefore address 32 CONSECUTIVE floats for any fixed position: x is re-read (an L2 hit, the
-//                        producer touched the tile microseconds earlier) and y = x * rsqrt(beta + acc) is written with fully
-//                        coalesced 128-byte warp accesses and no shared-memory transpose -> mbarrier tmem_empty[a]
+//                        2 * C/8 tcgen05.mma kind::tf32 per M block; tcgen05.commit -> empty[s] and tmem_full[a]
+//   epilogue warps (8)   tcgen05.ld: lane = output channel, columns = positions.  With channels-last activations the lanes of a
+//                        warp therefore address CONSECUTIVE floats for any fixed position: x is re-read (an L2 hit: the producer
+//                        touched the tile microseconds earlier with a normal-priority load) and y = x * rsqrt(beta + acc) is
+//                        written with coalesced warp accesses and no shared-memory transpose -> mbarrier tmem_empty[a]
 //
-// gamma is the A operand (M = 128 output channels, rows >= C zero-padded), the x^2 tile is the B operand (N = 128 positions).
-// The orientation is what removes the transpose of the first version (its TMEM lanes were positions, so a thread held 32
-// channels of ONE position and had to go through padded shared memory to store coalesced).
-// HBM traffic stays at the algorithmic 8 B/element; the epilogue's second read of x is L2 traffic.
+// gamma is the A operand (M = output channels), the x^2 tile is the B operand (N = positions).  That orientation is what removes
+// the transpose of the first version (its TMEM lanes were positions, so a thread held 32 channels of ONE position and had to go
+// through padded shared memory to store coalesced).
+//   C <= 128: one M = 128 block (rows >= C zero-padded), TN = 128 positions per tile.
+//   C == 192: gamma (144 KB) still fits beside one x^2 stage when TN = 48: an M = 128 block (channels 0..127) plus an M = 64
+//             block (channels 128..191; its accumulator rows live in lanes 32*(j/16) + j%16, i.e. the low half of each warp's
+//             TMEM quadrant).  This covers the N = 192 model of BASELINE.json configs[3].
+// HBM traffic stays at the algorithmic 8 B/element; the epilogue's second read of x is L2 traffic (ncu: profiles/).
 #include "umma.cuh"
 
 namespace sic {
@@ -26,65 +30,112 @@ namespace {
 
 using namespace umma;
 
-constexpr int kTileN = 128;                 // positions per tile == UMMA N
-constexpr int kRowsA = 128;                 // UMMA M: output channels, zero-padded
 constexpr int kEpiWarps = 8, kProdWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32, kProdThreads = kProdWarps * 32;
 constexpr int kThreadsWS = kEpiThreads + kProdThreads + 32;   // + the MMA warp
-constexpr int kAccCols = 128;               // TMEM columns per accumulator stage (= kTileN)
+constexpr int kAccCols = 128;               // TMEM columns per accumulator stage (block B at +64)
+constexpr int kColsB = 64;
 constexpr float kReparamOffset = 3.814697265625e-06f;  // 2^-18, layers.py:8
 
-__host__ __device__ constexpr int ws_stages(int C) { return ((size_t)kRowsA * C * 4 * 5 + 1024 <= 227u * 1024u) ? 2 : 1; }
-__host__ __device__ constexpr size_t ws_smem_bytes(int C) { return (size_t)kRowsA * C * 4 * (1 + 2 * ws_stages(C)) + 1024; }
+template <int C>
+struct WsCfg {
+    static constexpr bool kTwoBlocks = C > 128;                     // C == 192: M = 128 block + M = 64 block
+    static constexpr int TN = kTwoBlocks ? 48 : 128;                // positions per tile == UMMA N
+    static constexpr int ROWS_G = kTwoBlocks ? C : 128;             // rows of the gamma operand per K-block
+    static constexpr int NP = TN / 2;                               // positions per epilogue warp
+    static constexpr uint32_t G_BYTES = ROWS_G * C * 4;
+    static constexpr uint32_t B_BYTES = TN * C * 4;                 // one of hi / lo
+    static constexpr int NS = ((size_t)G_BYTES + 4 * (size_t)B_BYTES + 1024 <= 227u * 1024u) ? 2 : 1;   // smem stages
+    static constexpr size_t SMEM = (size_t)G_BYTES + (size_t)NS * 2 * B_BYTES + 1024;
+    static_assert(C % 32 == 0 && (C <= 128 || C == 192), "dense GDN kernel: C in {32,64,96,128,192}");
+    static_assert((TN * (C / 4)) % kProdThreads == 0, "producer threads must tile the x block");
+    static_assert(SMEM <= 227u * 1024u, "operands do not fit in shared memory");
+};
 
-// One epilogue warp, one half tile: 64 positions of this lane's output channel.  x is requested before the accumulator barrier
-// is awaited so the L2 latency hides behind the MMA; FULL = all 64 positions exist (no predicates on the fast path).
-template <int C, bool INVERSE, bool FULL>
-__device__ __forceinline__ void epilogue_half(const float *__restrict__ xp, float *__restrict__ yp, int left, float beta,
-                                              uint32_t taddr, uint32_t bar, uint32_t parity) {
-    float xv[64];
+__device__ __forceinline__ float4 ldg_keep(const float4 *p) {   // read-only path, NORMAL L2 priority (the epilogue re-reads the tile)
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+template <bool INVERSE>
+__device__ __forceinline__ float norm_factor(float s) {
+    float d;
+    if (INVERSE) asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(s));
+    else asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(s));
+    return d;
+}
+
+// One accumulator block of one epilogue warp: NP positions of this lane's output channel.  x was requested before the
+// accumulator barrier was awaited, so its L2 latency hides behind the MMA.  FULL = all NP positions exist.
+template <int C, int NP, bool INVERSE, bool FULL>
+__device__ __forceinline__ void epilogue_block(const float (&xv)[NP], float *__restrict__ yp, int left, float beta, uint32_t taddr,
+                                               bool lane_ok) {
+    static_assert(NP % 8 == 0, "epilogue chunks are 16 or 8 columns");
 #pragma unroll
-    for (int j = 0; j < 64; ++j) xv[j] = (FULL || j < left) ? __ldcg(xp + (long)j * C) : 0.f;
-    mbar_wait(bar, parity);
-    fence_after_sync();
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int k0 = 0; k0 + 16 <= NP; k0 += 16) {
         float acc[16];
-        tmem_ld16(taddr + ch * 16, acc);
+        tmem_ld16(taddr + k0, acc);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const float s = beta + acc[j];
-            float d;
-            if (INVERSE) asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(s));
-            else asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(s));
-            const int k = ch * 16 + j;
-            if (FULL || k < left) __stcs(yp + (long)k * C, xv[k] * d);
+            const int k = k0 + j;
+            if (lane_ok && (FULL || k < left)) __stcs(yp + (long)k * C, xv[k] * norm_factor<INVERSE>(beta + acc[j]));
         }
     }
+    if constexpr (NP % 16 != 0) {
+        constexpr int k0 = NP - 8;
+        float acc[8];
+        tmem_ld8(taddr + k0, acc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j;
+            if (lane_ok && (FULL || k < left)) __stcs(yp + (long)k * C, xv[k] * norm_factor<INVERSE>(beta + acc[j]));
+        }
+    }
+}
+
+template <int C, bool INVERSE, bool FULL>
+__device__ __forceinline__ void epilogue_tile(const float *__restrict__ x, float *__restrict__ y, long p0, int left, int cA, bool okA,
+                                              float betaA, int cB, bool okB, float betaB, uint32_t taddr, uint32_t bar,
+                                              uint32_t parity) {
+    using Cfg = WsCfg<C>;
+    constexpr int NP = Cfg::NP;
+    float xa[NP], xb[Cfg::kTwoBlocks ? NP : 1];
+    const float *xpA = x + p0 * C + cA, *xpB = x + p0 * C + cB;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) xa[j] = (okA && (FULL || j < left)) ? __ldcg(xpA + (long)j * C) : 0.f;
+    if (Cfg::kTwoBlocks) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) xb[j] = (okB && (FULL || j < left)) ? __ldcg(xpB + (long)j * C) : 0.f;
+    }
+    mbar_wait(bar, parity);
+    fence_after_sync();
+    epilogue_block<C, NP, INVERSE, FULL>(xa, y + p0 * C + cA, left, betaA, taddr, okA);
+    if constexpr (Cfg::kTwoBlocks) epilogue_block<C, NP, INVERSE, FULL>(xb, y + p0 * C + cB, left, betaB, taddr + kColsB, okB);
 }
 
 template <int C, bool INVERSE>
 __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float *__restrict__ x, const float *__restrict__ beta_param,
                                                                      const float *__restrict__ gamma_param, long P,
                                                                      float *__restrict__ y) {
-    static_assert(C % 32 == 0 && C >= 32 && C <= 128, "dense GDN kernel: C in {32,64,96,128}");
+    using Cfg = WsCfg<C>;
     constexpr int KB = C / 32;                       // K-blocks of 32 fp32 (one 128-byte swizzle row)
     constexpr int V = C / 4;                         // float4 per position
-    constexpr int NS = ws_stages(C);                 // shared-memory stages of (hi, lo)
-    constexpr uint32_t OPER_BYTES = kRowsA * C * 4;  // one K-major operand of 128 rows
-    constexpr int PER = kTileN * V / kProdThreads;   // float4 per producer thread per tile
+    constexpr int TN = Cfg::TN, NS = Cfg::NS, ROWS_G = Cfg::ROWS_G, NP = Cfg::NP;
+    constexpr uint32_t B_BYTES = Cfg::B_BYTES;
+    constexpr int PER = TN * V / kProdThreads;       // float4 per producer thread per tile
     extern __shared__ uint8_t smem_raw[];
     // 32-bit shared-window addresses throughout (st.shared, descriptors); SWIZZLE_128B operands need 1024-byte alignment
-    const uint32_t sG = (smem_u32(smem_raw) + 1023u) & ~1023u;   // [128 x C]  gamma, re-parameterised
-    const uint32_t sStage = sG + OPER_BYTES;                     // NS x { hi [128 x C], lo [128 x C] }
-    __shared__ __align__(8) uint64_t bars[2 * NS + 4];   // full[NS], empty[NS], tmem_full[2], tmem_empty[2]
+    const uint32_t sG = (smem_u32(smem_raw) + 1023u) & ~1023u;   // [ROWS_G x C]  gamma, re-parameterised
+    const uint32_t sStage = sG + Cfg::G_BYTES;                   // NS x { hi [TN x C], lo [TN x C] }
+    __shared__ __align__(8) uint64_t bars[2 * NS + 4];           // full[NS], empty[NS], tmem_full[2], tmem_empty[2]
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NS]);
     const uint32_t bar_tfull = smem_u32(&bars[2 * NS]), bar_tempty = smem_u32(&bars[2 * NS + 2]);
 
     // ---- one-time setup: gamma -> A operand (layers.py:21 applied to the C x C matrix), barriers, TMEM
-    for (int idx = tid; idx < kRowsA * V; idx += kThreadsWS) {
+    for (int idx = tid; idx < ROWS_G * V; idx += kThreadsWS) {
         const int i = idx / V, c4 = idx - i * V;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < C) {
@@ -92,7 +143,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
             g.x = g.x * g.x - kReparamOffset; g.y = g.y * g.y - kReparamOffset;
             g.z = g.z * g.z - kReparamOffset; g.w = g.w * g.w - kReparamOffset;
         }
-        sts128(sG + sw128_offset(i, c4 >> 3, c4 & 7, kRowsA), g);
+        sts128(sG + sw128_offset(i, c4 >> 3, c4 & 7, ROWS_G), g);
     }
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
@@ -114,31 +165,37 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_slot;
-    const long n_tiles = (P + kTileN - 1) / kTileN;
+    const long n_tiles = (P + TN - 1) / TN;
 
     if (warp < kEpiWarps) {
         // ===================================================== epilogue: TMEM -> y
         const int q = warp & 3;                      // TMEM lane quadrant this warp may read (hardware rule: warp id % 4)
-        const int col0 = (warp >> 2) * 64;           // its half of the 128 position columns
-        const int c = q * 32 + lane;                 // output channel of this lane
-        const bool ch_ok = q * 32 < C;               // warp-uniform (C is a multiple of 32); idle warps only keep the barriers in step
-        float beta = 1.f;
-        if (ch_ok) {
-            const float b = __ldg(beta_param + c);
-            beta = b * b - kReparamOffset;           // layers.py:20
+        const int col0 = (warp >> 2) * NP;           // its half of the TN position columns
+        const int cA = q * 32 + lane;                // block A (M = 128): accumulator row = lane of the quadrant
+        const bool okA = q * 32 < C;                 // warp-uniform (C is a multiple of 32); idle warps only keep the barriers in step
+        const int cB = 128 + q * 16 + (lane & 15);   // block B (M = 64): row j lives in lane 32*(j/16) + j%16
+        const bool okB = Cfg::kTwoBlocks && lane < 16;
+        float betaA = 1.f, betaB = 1.f;
+        if (okA) {
+            const float b = __ldg(beta_param + cA);
+            betaA = b * b - kReparamOffset;          // layers.py:20
+        }
+        if (okB) {
+            const float b = __ldg(beta_param + cB);
+            betaB = b * b - kReparamOffset;
         }
         long it = 0;
         for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t a = (uint32_t)(it & 1), aph = (uint32_t)((it >> 1) & 1);
-            const long p0 = tile * kTileN + col0;
+            const long p0 = tile * TN + col0;
             const long left = P - p0;                // positions of this half that exist (may be <= 0 on the last tile)
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccCols + (uint32_t)col0;
-            if (!ch_ok || left <= 0) {
+            if (!okA || left <= 0) {
                 mbar_wait(bar_tfull + 8 * a, aph);
-            } else if (left >= 64) {
-                epilogue_half<C, INVERSE, true>(x + p0 * C + c, y + p0 * C + c, 64, beta, taddr, bar_tfull + 8 * a, aph);
+            } else if (left >= NP) {
+                epilogue_tile<C, INVERSE, true>(x, y, p0, NP, cA, okA, betaA, cB, okB, betaB, taddr, bar_tfull + 8 * a, aph);
             } else {
-                epilogue_half<C, INVERSE, false>(x + p0 * C + c, y + p0 * C + c, (int)left, beta, taddr, bar_tfull + 8 * a, aph);
+                epilogue_tile<C, INVERSE, false>(x, y, p0, (int)left, cA, okA, betaA, cB, okB, betaB, taddr, bar_tfull + 8 * a, aph);
             }
             fence_before_sync();
             mbar_arrive(bar_tempty + 8 * a);         // accumulator stage a may be overwritten
@@ -148,20 +205,30 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
         const int ptid = tid - kEpiThreads;
         float4 xn[PER];
         auto request = [&](long t) {
-            const long q0 = t * kTileN;
+            const long q0 = t * TN;
             const long vld = P - q0;                 // <= 0 past the end
             const float4 *src = reinterpret_cast<const float4 *>(x + q0 * C);
 #pragma unroll
             for (int k = 0; k < PER; ++k) {
                 const int idx = ptid + k * kProdThreads, r = idx / V;
-                xn[k] = (r < vld) ? ldg_stream(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xn[k] = (r < vld) ? ldg_keep(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        // DRAM latency is taken by an L2 prefetch two tiles ahead (one thread, one bulk instruction, no registers); the register
+        // loads one tile ahead then hit L2, so the in-flight window is no longer bounded by the producers' register file
+        auto prefetch = [&](long t) {
+            const long q0 = t * TN;
+            if (ptid == 0 && q0 < P) {
+                const long rows = (P - q0 < TN) ? (P - q0) : TN;
+                prefetch_l2_bulk(x + q0 * C, (uint32_t)(rows * C * 4));
             }
         };
         request(blockIdx.x);
+        prefetch(blockIdx.x + (long)gridDim.x);
         long it = 0;
         for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t s = (uint32_t)(it % NS), ph = (uint32_t)((it / NS) & 1);
-            const uint32_t sHi = sStage + s * 2 * OPER_BYTES, sLo = sHi + OPER_BYTES;
+            const uint32_t sHi = sStage + s * 2 * B_BYTES, sLo = sHi + B_BYTES;
             mbar_wait(bar_empty + 8 * s, ph ^ 1);    // the MMAs that read this stage have completed
 #pragma unroll
             for (int k = 0; k < PER; ++k) {
@@ -173,28 +240,29 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
                 hi.y = __uint_as_float(__float_as_uint(sq.y) & 0xFFFFE000u); lo.y = sq.y - hi.y;
                 hi.z = __uint_as_float(__float_as_uint(sq.z) & 0xFFFFE000u); lo.z = sq.z - hi.z;
                 hi.w = __uint_as_float(__float_as_uint(sq.w) & 0xFFFFE000u); lo.w = sq.w - hi.w;
-                const uint32_t off = sw128_offset(r, c4 >> 3, c4 & 7, kTileN);
+                const uint32_t off = sw128_offset(r, c4 >> 3, c4 & 7, TN);
                 sts128(sHi + off, hi);
                 sts128(sLo + off, lo);
             }
             fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core's async proxy
             mbar_arrive(bar_full + 8 * s);
-            request(tile + gridDim.x);               // next tile's HBM reads fly while the MMA and the epilogue run
+            request(tile + gridDim.x);               // next tile (prefetched into L2 one iteration ago) -> registers
+            prefetch(tile + 2 * (long)gridDim.x);
         }
     } else {
-        // ===================================================== MMA warp: every lane follows the barriers, lane 0 issues
-        const uint32_t idesc = idesc_tf32(kRowsA, kTileN);
-        const uint64_t descG = smem_desc(sG);
+        // ===================================================== MMA warp: every lane follows the barriers, one elected lane issues
+        const uint32_t idescA = idesc_tf32(128, TN), idescB = idesc_tf32(64, TN);
+        const uint64_t descGA = smem_desc(sG), descGB = smem_desc(sG + (128 / 8) * 1024);   // block B starts at gamma row 128
         long it = 0;
         for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t s = (uint32_t)(it % NS), ph = (uint32_t)((it / NS) & 1);
             const uint32_t a = (uint32_t)(it & 1), aph = (uint32_t)((it >> 1) & 1);
-            const uint32_t sHi = sStage + s * 2 * OPER_BYTES;
-            const uint64_t descHi = smem_desc(sHi), descLo = smem_desc(sHi + OPER_BYTES);
+            const uint32_t sHi = sStage + s * 2 * B_BYTES;
+            const uint64_t descHi = smem_desc(sHi), descLo = smem_desc(sHi + B_BYTES);
             mbar_wait(bar_tempty + 8 * a, aph ^ 1);  // the epilogue has drained this accumulator stage
             mbar_wait(bar_full + 8 * s, ph);         // x^2 of this tile is in shared memory
             fence_after_sync();
-            if (lane == 0) {
+            if (elect_one_sync()) {
                 const uint32_t tmem_d = tmem_base + a * kAccCols;
                 uint32_t accumulate = 0;
 #pragma unroll
@@ -204,8 +272,10 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
                     for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {     // 4 x (8 tf32 = 32 B) inside one 128-byte swizzle row
-                            const uint64_t adv = (uint64_t)((kb * (kRowsA * 128) + ks * 32) >> 4);
-                            mma_tf32(tmem_d, descG + adv, dB + adv, idesc, accumulate);
+                            const uint64_t advG = (uint64_t)((kb * (ROWS_G * 128) + ks * 32) >> 4);
+                            const uint64_t advB = (uint64_t)((kb * (TN * 128) + ks * 32) >> 4);
+                            mma_tf32(tmem_d, descGA + advG, dB + advB, idescA, accumulate);
+                            if (Cfg::kTwoBlocks) mma_tf32(tmem_d + kColsB, descGB + advG, dB + advB, idescB, accumulate);
                             accumulate = 1;
                         }
                     }
@@ -226,14 +296,14 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
 
 template <int C>
 int launch_dense_ws(const float *x, const float *beta_param, const float *gamma_param, long P, int inverse, float *y, cudaStream_t st) {
-    const size_t smem = ws_smem_bytes(C);
+    const size_t smem = WsCfg<C>::SMEM;
     auto kern = inverse ? gdn_dense_ws_kernel<C, true> : gdn_dense_ws_kernel<C, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         set_error("sic_gdn_dense_fwd (pipelined): cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
         return (int)e;
     }
-    const long n_tiles = (P + kTileN - 1) / kTileN;
+    const long n_tiles = (P + WsCfg<C>::TN - 1) / WsCfg<C>::TN;
     const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());   // persistent: one CTA per SM
     kern<<<grid, kThreadsWS, smem, st>>>(x, beta_param, gamma_param, P, y);
     SIC_CHECK_LAUNCH("sic_gdn_dense_fwd (pipelined)");
@@ -249,9 +319,10 @@ int gdn_dense_ws_dispatch(const float *x, const float *beta_param, const float *
         case 64: return launch_dense_ws<64>(x, beta_param, gamma_param, positions, inverse, y, st);
         case 96: return launch_dense_ws<96>(x, beta_param, gamma_param, positions, inverse, y, st);
         case 128: return launch_dense_ws<128>(x, beta_param, gamma_param, positions, inverse, y, st);
+        case 192: return launch_dense_ws<192>(x, beta_param, gamma_param, positions, inverse, y, st);
         default:
-            set_error("sic_gdn_dense_fwd: C=%d unsupported (gamma and the x^2 hi/lo tile are resident in shared memory: C in "
-                      "{32,64,96,128}; wider layers need K-streaming)", C);
+            set_error("sic_gdn_dense_fwd: C=%d unsupported (gamma and one x^2 hi/lo tile must be resident in shared memory: "
+                      "C in {32,64,96,128,192})", C);
             return SIC_E_UNSUPPORTED;
     }
 }

@@ -100,7 +100,8 @@ int sic_gdn_bwd(const float *x, const float *bias, const float *g, const float *
  *   x, y: CHANNELS-LAST activations viewed as [positions, C] (positions = B*H*W); beta_param [C] and gamma_param [C,C]
  *   (row i = output channel) are the stored parameters, re-parameterised inside like layers.py:20-21.
  *   tcgen05.mma kind::tf32 with an exact hi/lo split of x^2: tolerance-only mode (gamma at TF32 precision).
- *   This build: C in {32, 64, 96, 128} (operands resident in shared memory), otherwise SIC_E_UNSUPPORTED. */
+ *   This build: C in {32, 64, 96, 128, 192} (gamma and one x^2 tile resident in shared memory; 192 only in the pipelined
+ *   kernel), otherwise SIC_E_UNSUPPORTED. */
 int sic_gdn_dense_fwd(const float *x, const float *beta_param, const float *gamma_param, long positions, int C, int inverse,
                       float *y, void *stream);
 /* The same operation with the kernel chosen explicitly (both are kept so each can be parity-tested and timed):

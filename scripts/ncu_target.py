@@ -37,5 +37,11 @@ if which in ("all", "dense"):
     gm = torch.sqrt(torch.rand(128, 128, device=dev) * 0.02 + torch.eye(128, device=dev) * 0.1 + 2.0 ** -18)
     for _ in range(reps):
         F.gdn_dense(x, beta, gm, False)
+if which in ("dense192",):
+    x = torch.randn(8, 192, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
+    beta = torch.sqrt(torch.rand(192, device=dev) + 0.5)
+    gm = torch.sqrt(torch.rand(192, 192, device=dev) * 0.02 + torch.eye(192, device=dev) * 0.1 + 2.0 ** -18)
+    for _ in range(reps):
+        F.gdn_dense(x, beta, gm, False)
 torch.cuda.synchronize()
 print("ok")

@@ -168,6 +168,17 @@ DENSE_VARIANTS = [0, 1]      # include/sic.h: SIC_DENSE_SERIAL, SIC_DENSE_PIPELI
 @pytest.mark.parametrize("shape", [(2, 128, 16, 24), (1, 64, 9, 7), (3, 32, 5, 5), (2, 96, 12, 12), (1, 128, 1, 3),
                                    (1, 128, 10, 20), (1, 96, 7, 13)])
 def test_dense_gdn_forward_vs_oracle(shape, inverse, variant):
+    _dense_forward_case(shape, inverse, variant)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", [(2, 192, 16, 24), (1, 192, 7, 13), (1, 192, 1, 5), (3, 192, 9, 9)])
+def test_dense_gdn_forward_c192_two_m_blocks(shape, inverse):
+    """C = 192 (the N = 192 model of BASELINE.json configs[3]): an M = 128 and an M = 64 tcgen05 block per 48-position tile."""
+    _dense_forward_case(shape, inverse, 1)
+
+
+def _dense_forward_case(shape, inverse, variant):
     """tcgen05 kernel vs the float64 oracle (F.conv2d(x^2, gamma, beta) semantics).  gamma is consumed at TF32 precision,
     so the tight comparison uses the oracle with gamma truncated to TF32; against the untruncated oracle the difference is
     the documented 2^-11 parameter perturbation."""
@@ -189,11 +200,14 @@ def test_dense_gdn_forward_vs_oracle(shape, inverse, variant):
 
 
 @pytest.mark.parametrize("variant", DENSE_VARIANTS)
-@pytest.mark.parametrize("C,positions", [(128, 148 * 128 * 3 + 77), (64, 148 * 128 * 5 + 64), (96, 148 * 128 * 2 + 1)])
+@pytest.mark.parametrize("C,positions", [(128, 148 * 128 * 3 + 77), (64, 148 * 128 * 5 + 64), (96, 148 * 128 * 2 + 1),
+                                         (192, 148 * 48 * 4 + 29)])
 def test_dense_gdn_many_tiles_per_cta(C, positions, variant):
     """More tiles than 2 x SMs: every persistent CTA wraps its shared-memory stage and both TMEM accumulator stages several
     times (the pipelined kernel's mbarrier phases), and the last tile is ragged.  The two kernels must also agree with each
     other to rounding (same hi/lo products, different summation engines only in the epilogue's rsqrt)."""
+    if C == 192 and variant == 0:
+        pytest.skip("the serial kernel keeps C <= 128")
     F = _F()
     rng = np.random.default_rng(C + positions)
     x = (rng.standard_normal((1, C, positions, 1)) * 2).astype(np.float32)
@@ -245,7 +259,7 @@ def test_dense_gdn_backward_and_module():
     assert m.gamma_conv.weight.grad is None                       # the diagonal conv is the unused one in dense mode
     with pytest.raises(sic.SicError):
         F = _F()
-        F.gdn_dense(torch.randn(1, 192, 4, 4, device="cuda"), torch.ones(192, device="cuda"), torch.ones(192, 192, device="cuda"))
+        F.gdn_dense(torch.randn(1, 160, 4, 4, device="cuda"), torch.ones(160, device="cuda"), torch.ones(160, 160, device="cuda"))
 
 
 @pytest.mark.parametrize("fmt", [torch.contiguous_format, torch.channels_last])
