@@ -23,6 +23,8 @@
 //             block (channels 128..191; its accumulator rows live in lanes 32*(j/16) + j%16, i.e. the low half of each warp's
 //             TMEM quadrant).  This covers the N = 192 model of BASELINE.json configs[3].
 // HBM traffic stays at the algorithmic 8 B/element; the epilogue's second read of x is L2 traffic (ncu: profiles/).
+#include <stdlib.h>
+
 #include "umma.cuh"
 
 namespace sic {
@@ -33,23 +35,31 @@ using namespace umma;
 constexpr int kEpiWarps = 8, kProdWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32, kProdThreads = kProdWarps * 32;
 constexpr int kThreadsWS = kEpiThreads + kProdThreads + 32;   // + the MMA warp
-constexpr int kAccCols = 128;               // TMEM columns per accumulator stage (block B at +64)
-constexpr int kColsB = 64;
+constexpr int kColsB = 128;                 // TMEM column offset of the M = 64 block inside an accumulator stage
 constexpr float kReparamOffset = 3.814697265625e-06f;  // 2^-18, layers.py:8
 
+// Tile geometry.  The K (input-channel) axis of a tile is fed to the tensor core in KS sub-steps of KBS 128-byte K-blocks, each
+// sub-step through one shared-memory stage, so the producers fill sub-step u+1 while the MMAs of sub-step u run.
 template <int C>
 struct WsCfg {
     static constexpr bool kTwoBlocks = C > 128;                     // C == 192: M = 128 block + M = 64 block
-    static constexpr int TN = kTwoBlocks ? 48 : 128;                // positions per tile == UMMA N
+    static constexpr int TN = kTwoBlocks ? 96 : 128;                // positions per tile == UMMA N
     static constexpr int ROWS_G = kTwoBlocks ? C : 128;             // rows of the gamma operand per K-block
     static constexpr int NP = TN / 2;                               // positions per epilogue warp
+    static constexpr int KB = C / 32;                               // K-blocks of 32 fp32 (one 128-byte swizzle row)
+    static constexpr int KS = C == 192 ? 6 : C == 128 ? 2 : C == 96 ? 3 : 1;   // sub-steps per tile
+    static constexpr int KBS = KB / KS;                             // K-blocks per sub-step
     static constexpr uint32_t G_BYTES = ROWS_G * C * 4;
-    static constexpr uint32_t B_BYTES = TN * C * 4;                 // one of hi / lo
-    static constexpr int NS = ((size_t)G_BYTES + 4 * (size_t)B_BYTES + 1024 <= 227u * 1024u) ? 2 : 1;   // smem stages
+    static constexpr uint32_t B_BYTES = TN * KBS * 128;             // one of hi / lo of one sub-step
+    static constexpr int NS_FIT = (int)((227u * 1024u - 1024u - G_BYTES) / (2 * B_BYTES));
+    static constexpr int NS = NS_FIT > 4 ? 4 : NS_FIT;              // shared-memory stages
     static constexpr size_t SMEM = (size_t)G_BYTES + (size_t)NS * 2 * B_BYTES + 1024;
+    static constexpr int ACC_COLS = kTwoBlocks ? 256 : 128;         // TMEM columns per accumulator stage
+    static constexpr int VH = KBS * 8;                              // float4 per position per sub-step
+    static constexpr int PER = TN * VH / kProdThreads;              // float4 per producer thread per sub-step
     static_assert(C % 32 == 0 && (C <= 128 || C == 192), "dense GDN kernel: C in {32,64,96,128,192}");
-    static_assert((TN * (C / 4)) % kProdThreads == 0, "producer threads must tile the x block");
-    static_assert(SMEM <= 227u * 1024u, "operands do not fit in shared memory");
+    static_assert(KB % KS == 0 && (TN * VH) % kProdThreads == 0, "producer threads must tile the sub-step");
+    static_assert(NS >= 1 && SMEM <= 227u * 1024u, "operands do not fit in shared memory");
 };
 
 __device__ __forceinline__ float4 ldg_keep(const float4 *p) {   // read-only path, NORMAL L2 priority (the epilogue re-reads the tile)
@@ -66,68 +76,64 @@ __device__ __forceinline__ float norm_factor(float s) {
     return d;
 }
 
-// One accumulator block of one epilogue warp: NP positions of this lane's output channel.  x was requested before the
-// accumulator barrier was awaited, so its L2 latency hides behind the MMA.  FULL = all NP positions exist.
-template <int C, int NP, bool INVERSE, bool FULL>
-__device__ __forceinline__ void epilogue_block(const float (&xv)[NP], float *__restrict__ yp, int left, float beta, uint32_t taddr,
-                                               bool lane_ok) {
-    static_assert(NP % 8 == 0, "epilogue chunks are 16 or 8 columns");
-#pragma unroll
-    for (int k0 = 0; k0 + 16 <= NP; k0 += 16) {
-        float acc[16];
-        tmem_ld16(taddr + k0, acc);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int k = k0 + j;
-            if (lane_ok && (FULL || k < left)) __stcs(yp + (long)k * C, xv[k] * norm_factor<INVERSE>(beta + acc[j]));
-        }
-    }
-    if constexpr (NP % 16 != 0) {
-        constexpr int k0 = NP - 8;
-        float acc[8];
-        tmem_ld8(taddr + k0, acc);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = k0 + j;
-            if (lane_ok && (FULL || k < left)) __stcs(yp + (long)k * C, xv[k] * norm_factor<INVERSE>(beta + acc[j]));
-        }
-    }
-}
-
+// Epilogue of one warp for one tile: NP positions of this lane's output channel (block A), then of its block-B channel when
+// C = 192.  x is fetched in batches of 16 positions through a 2-deep register ring: the first two batches are requested before
+// the accumulator barrier is awaited (their L2 latency hides behind the MMA), every later batch while the two before it are being
+// normalised and stored.  32 + 16 live values keep the role inside the 96-register budget of a 17-warp CTA without spills
+// (spill traffic shares the L1 data pipe with the tensor core's operand reads, which is this kernel's critical resource).
 template <int C, bool INVERSE, bool FULL>
 __device__ __forceinline__ void epilogue_tile(const float *__restrict__ x, float *__restrict__ y, long p0, int left, int cA, bool okA,
                                               float betaA, int cB, bool okB, float betaB, uint32_t taddr, uint32_t bar,
                                               uint32_t parity) {
     using Cfg = WsCfg<C>;
     constexpr int NP = Cfg::NP;
-    float xa[NP], xb[Cfg::kTwoBlocks ? NP : 1];
-    const float *xpA = x + p0 * C + cA, *xpB = x + p0 * C + cB;
+    static_assert(NP % 16 == 0, "epilogue batches are 16 columns");
+    constexpr int NBB = NP / 16;                                 // batches per block
+    constexpr int NB = Cfg::kTwoBlocks ? 2 * NBB : NBB;
+    const float *xA = x + p0 * C + cA, *xB = x + p0 * C + cB;
+    float *yA = y + p0 * C + cA, *yB = y + p0 * C + cB;
+    float ring[2][16];
+    auto load = [&](float (&dst)[16], int b) {
+        const bool blkB = b >= NBB;
+        const int k0 = (blkB ? b - NBB : b) * 16;
+        const float *src = blkB ? xB : xA;
+        const bool ok = blkB ? okB : okA;
 #pragma unroll
-    for (int j = 0; j < NP; ++j) xa[j] = (okA && (FULL || j < left)) ? __ldcg(xpA + (long)j * C) : 0.f;
-    if (Cfg::kTwoBlocks) {
-#pragma unroll
-        for (int j = 0; j < NP; ++j) xb[j] = (okB && (FULL || j < left)) ? __ldcg(xpB + (long)j * C) : 0.f;
-    }
+        for (int j = 0; j < 16; ++j) dst[j] = (ok && (FULL || k0 + j < left)) ? __ldcg(src + (long)(k0 + j) * C) : 0.f;
+    };
+    load(ring[0], 0);
+    if (NB > 1) load(ring[1], 1);
     mbar_wait(bar, parity);
     fence_after_sync();
-    epilogue_block<C, NP, INVERSE, FULL>(xa, y + p0 * C + cA, left, betaA, taddr, okA);
-    if constexpr (Cfg::kTwoBlocks) epilogue_block<C, NP, INVERSE, FULL>(xb, y + p0 * C + cB, left, betaB, taddr + kColsB, okB);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const bool blkB = b >= NBB;
+        const int k0 = (blkB ? b - NBB : b) * 16;
+        float *dst = blkB ? yB : yA;
+        const bool ok = blkB ? okB : okA;
+        const float beta = blkB ? betaB : betaA;
+        float acc[16];
+        tmem_ld16(taddr + (blkB ? kColsB : 0) + k0, acc);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (ok && (FULL || k0 + j < left)) __stcs(dst + (long)(k0 + j) * C, ring[b & 1][j] * norm_factor<INVERSE>(beta + acc[j]));
+        if (b + 2 < NB) load(ring[b & 1], b + 2);
+    }
 }
 
 template <int C, bool INVERSE>
 __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float *__restrict__ x, const float *__restrict__ beta_param,
-                                                                     const float *__restrict__ gamma_param, long P,
-                                                                     float *__restrict__ y) {
+                                                                     const float *__restrict__ gamma_param, long P, int use_prefetch,
+                                                                     int gamma_in_tmem, float *__restrict__ y) {
     using Cfg = WsCfg<C>;
-    constexpr int KB = C / 32;                       // K-blocks of 32 fp32 (one 128-byte swizzle row)
     constexpr int V = C / 4;                         // float4 per position
-    constexpr int TN = Cfg::TN, NS = Cfg::NS, ROWS_G = Cfg::ROWS_G, NP = Cfg::NP;
+    constexpr int TN = Cfg::TN, NS = Cfg::NS, ROWS_G = Cfg::ROWS_G, NP = Cfg::NP, KS = Cfg::KS, KBS = Cfg::KBS;
+    constexpr int VH = Cfg::VH, PER = Cfg::PER, ACC_COLS = Cfg::ACC_COLS;
     constexpr uint32_t B_BYTES = Cfg::B_BYTES;
-    constexpr int PER = TN * V / kProdThreads;       // float4 per producer thread per tile
     extern __shared__ uint8_t smem_raw[];
     // 32-bit shared-window addresses throughout (st.shared, descriptors); SWIZZLE_128B operands need 1024-byte alignment
     const uint32_t sG = (smem_u32(smem_raw) + 1023u) & ~1023u;   // [ROWS_G x C]  gamma, re-parameterised
-    const uint32_t sStage = sG + Cfg::G_BYTES;                   // NS x { hi [TN x C], lo [TN x C] }
+    const uint32_t sStage = sG + Cfg::G_BYTES;                   // NS x { hi [TN x 32 KBS], lo [TN x 32 KBS] }
     __shared__ __align__(8) uint64_t bars[2 * NS + 4];           // full[NS], empty[NS], tmem_full[2], tmem_empty[2]
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -156,8 +162,13 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    // TMEM: two accumulator stages, plus (one-block shapes, gamma_in_tmem) a copy of gamma as the A operand of a
+    // tensor-memory-sourced MMA: the tensor core then reads only the x^2 tile from shared memory, which halves its share of the
+    // L1/shared data pipe (ncu: that pipe, shared with the producers' stores and the epilogue's accesses, is the busiest unit)
+    constexpr uint32_t TMEM_COLS = Cfg::kTwoBlocks ? 2 * ACC_COLS : 512;
+    const bool a_tmem = !Cfg::kTwoBlocks && gamma_in_tmem != 0;
     if (warp == kEpiWarps + kProdWarps) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_slot)), "r"(2 * kAccCols));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
     fence_proxy_async();                             // gamma was written by the generic proxy, the MMA reads through the async proxy
@@ -165,6 +176,30 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t tmem_gamma = tmem_base + 2 * ACC_COLS;   // lane = output channel, column = input channel
+    if (a_tmem) {
+        if (warp < 4) {                              // one warp per TMEM lane quadrant: row = 32 * warp + lane
+            const int row = warp * 32 + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                float g[32];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (row < C) {
+                        v = __ldg(reinterpret_cast<const float4 *>(gamma_param + (size_t)row * C + c0) + j4);
+                        v.x = v.x * v.x - kReparamOffset; v.y = v.y * v.y - kReparamOffset;
+                        v.z = v.z * v.z - kReparamOffset; v.w = v.w * v.w - kReparamOffset;
+                    }
+                    g[4 * j4] = v.x; g[4 * j4 + 1] = v.y; g[4 * j4 + 2] = v.z; g[4 * j4 + 3] = v.w;
+                }
+                tmem_st32(tmem_gamma + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, g);
+            }
+        }
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+    }
     const long n_tiles = (P + TN - 1) / TN;
 
     if (warp < kEpiWarps) {
@@ -189,7 +224,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
             const uint32_t a = (uint32_t)(it & 1), aph = (uint32_t)((it >> 1) & 1);
             const long p0 = tile * TN + col0;
             const long left = P - p0;                // positions of this half that exist (may be <= 0 on the last tile)
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * kAccCols + (uint32_t)col0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * ACC_COLS + (uint32_t)col0;
             if (!okA || left <= 0) {
                 mbar_wait(bar_tfull + 8 * a, aph);
             } else if (left >= NP) {
@@ -201,97 +236,128 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
             mbar_arrive(bar_tempty + 8 * a);         // accumulator stage a may be overwritten
         }
     } else if (warp < kEpiWarps + kProdWarps) {
-        // ===================================================== producer: x -> x^2 (hi, lo) -> smem
+        // ===================================================== producer: x -> x^2 (hi, lo) -> smem, one K sub-step at a time
         const int ptid = tid - kEpiThreads;
         float4 xn[PER];
-        auto request = [&](long t) {
+        auto request = [&](long t, int h) {          // channels [h*32*KBS, (h+1)*32*KBS) of the TN positions of tile t -> registers
             const long q0 = t * TN;
             const long vld = P - q0;                 // <= 0 past the end
-            const float4 *src = reinterpret_cast<const float4 *>(x + q0 * C);
+            const float4 *src = reinterpret_cast<const float4 *>(x + q0 * C) + h * VH;
 #pragma unroll
             for (int k = 0; k < PER; ++k) {
-                const int idx = ptid + k * kProdThreads, r = idx / V;
-                xn[k] = (r < vld) ? ldg_keep(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int idx = ptid + k * kProdThreads, r = idx / VH, c4 = idx - r * VH;
+                xn[k] = (r < vld) ? ldg_keep(src + (long)r * V + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         // DRAM latency is taken by an L2 prefetch two tiles ahead (one thread, one bulk instruction, no registers); the register
-        // loads one tile ahead then hit L2, so the in-flight window is no longer bounded by the producers' register file
+        // loads one sub-step ahead then hit L2, so the in-flight window is not bounded by the producers' register file
         auto prefetch = [&](long t) {
             const long q0 = t * TN;
-            if (ptid == 0 && q0 < P) {
+            if (use_prefetch && ptid == 0 && q0 < P) {
                 const long rows = (P - q0 < TN) ? (P - q0) : TN;
                 prefetch_l2_bulk(x + q0 * C, (uint32_t)(rows * C * 4));
             }
         };
-        request(blockIdx.x);
+        request(blockIdx.x, 0);
         prefetch(blockIdx.x + (long)gridDim.x);
-        long it = 0;
-        for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const uint32_t s = (uint32_t)(it % NS), ph = (uint32_t)((it / NS) & 1);
-            const uint32_t sHi = sStage + s * 2 * B_BYTES, sLo = sHi + B_BYTES;
-            mbar_wait(bar_empty + 8 * s, ph ^ 1);    // the MMAs that read this stage have completed
+        uint32_t u = 0;                              // sub-step counter: stage = u % NS, phase = (u / NS) & 1
+        for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+            for (int h = 0; h < KS; ++h, ++u) {
+                const uint32_t s = u % NS, ph = (u / NS) & 1;
+                const uint32_t sHi = sStage + s * 2 * B_BYTES, sLo = sHi + B_BYTES;
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);    // the MMAs that read this stage have completed
 #pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                const int idx = ptid + k * kProdThreads, r = idx / V, c4 = idx - r * V;
-                const float4 v = xn[k];
-                const float4 sq = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
-                float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(sq.x) & 0xFFFFE000u); lo.x = sq.x - hi.x;
-                hi.y = __uint_as_float(__float_as_uint(sq.y) & 0xFFFFE000u); lo.y = sq.y - hi.y;
-                hi.z = __uint_as_float(__float_as_uint(sq.z) & 0xFFFFE000u); lo.z = sq.z - hi.z;
-                hi.w = __uint_as_float(__float_as_uint(sq.w) & 0xFFFFE000u); lo.w = sq.w - hi.w;
-                const uint32_t off = sw128_offset(r, c4 >> 3, c4 & 7, TN);
-                sts128(sHi + off, hi);
-                sts128(sLo + off, lo);
+                for (int k = 0; k < PER; ++k) {
+                    const int idx = ptid + k * kProdThreads, r = idx / VH, c4 = idx - r * VH;
+                    const float4 v = xn[k];
+                    const float4 sq = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+                    float4 hi, lo;
+                    hi.x = __uint_as_float(__float_as_uint(sq.x) & 0xFFFFE000u); lo.x = sq.x - hi.x;
+                    hi.y = __uint_as_float(__float_as_uint(sq.y) & 0xFFFFE000u); lo.y = sq.y - hi.y;
+                    hi.z = __uint_as_float(__float_as_uint(sq.z) & 0xFFFFE000u); lo.z = sq.z - hi.z;
+                    hi.w = __uint_as_float(__float_as_uint(sq.w) & 0xFFFFE000u); lo.w = sq.w - hi.w;
+                    const uint32_t off = sw128_offset(r, c4 >> 3, c4 & 7, TN);
+                    sts128(sHi + off, hi);
+                    sts128(sLo + off, lo);
+                }
+                fence_proxy_async();                 // generic-proxy writes -> visible to the tensor core's async proxy
+                mbar_arrive(bar_full + 8 * s);
+                if (h + 1 < KS) {
+                    request(tile, h + 1);            // next K sub-step of this tile
+                } else {
+                    request(tile + gridDim.x, 0);    // next tile (prefetched into L2 one tile ago)
+                    prefetch(tile + 2 * (long)gridDim.x);
+                }
             }
-            fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core's async proxy
-            mbar_arrive(bar_full + 8 * s);
-            request(tile + gridDim.x);               // next tile (prefetched into L2 one iteration ago) -> registers
-            prefetch(tile + 2 * (long)gridDim.x);
         }
     } else {
         // ===================================================== MMA warp: every lane follows the barriers, one elected lane issues
         const uint32_t idescA = idesc_tf32(128, TN), idescB = idesc_tf32(64, TN);
         const uint64_t descGA = smem_desc(sG), descGB = smem_desc(sG + (128 / 8) * 1024);   // block B starts at gamma row 128
         long it = 0;
+        uint32_t u = 0;
         for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const uint32_t s = (uint32_t)(it % NS), ph = (uint32_t)((it / NS) & 1);
             const uint32_t a = (uint32_t)(it & 1), aph = (uint32_t)((it >> 1) & 1);
-            const uint32_t sHi = sStage + s * 2 * B_BYTES;
-            const uint64_t descHi = smem_desc(sHi), descLo = smem_desc(sHi + B_BYTES);
+            const uint32_t tmem_d = tmem_base + a * ACC_COLS;
             mbar_wait(bar_tempty + 8 * a, aph ^ 1);  // the epilogue has drained this accumulator stage
-            mbar_wait(bar_full + 8 * s, ph);         // x^2 of this tile is in shared memory
-            fence_after_sync();
-            if (elect_one_sync()) {
-                const uint32_t tmem_d = tmem_base + a * kAccCols;
-                uint32_t accumulate = 0;
 #pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    const uint64_t dB = pass == 0 ? descHi : descLo;
+            for (int h = 0; h < KS; ++h, ++u) {
+                const uint32_t s = u % NS, ph = (u / NS) & 1;
+                const uint32_t sHi = sStage + s * 2 * B_BYTES;
+                const uint64_t descHi = smem_desc(sHi), descLo = smem_desc(sHi + B_BYTES);
+                mbar_wait(bar_full + 8 * s, ph);     // x^2 of this sub-step is in shared memory
+                fence_after_sync();
+                if (elect_one_sync()) {
 #pragma unroll
-                    for (int kb = 0; kb < KB; ++kb) {
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const uint64_t dB = pass == 0 ? descHi : descLo;
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {     // 4 x (8 tf32 = 32 B) inside one 128-byte swizzle row
-                            const uint64_t advG = (uint64_t)((kb * (ROWS_G * 128) + ks * 32) >> 4);
-                            const uint64_t advB = (uint64_t)((kb * (TN * 128) + ks * 32) >> 4);
-                            mma_tf32(tmem_d, descGA + advG, dB + advB, idescA, accumulate);
-                            if (Cfg::kTwoBlocks) mma_tf32(tmem_d + kColsB, descGB + advG, dB + advB, idescB, accumulate);
-                            accumulate = 1;
+                        for (int kb = 0; kb < KBS; ++kb) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {     // 4 x (8 tf32 = 32 B) inside one 128-byte swizzle row
+                                const uint64_t advG = (uint64_t)((((h * KBS + kb) * (ROWS_G * 128)) + ks * 32) >> 4);
+                                const uint64_t advB = (uint64_t)((kb * (TN * 128) + ks * 32) >> 4);
+                                const uint32_t accumulate = (h | pass | kb | ks) != 0;
+                                if (a_tmem) mma_tf32_ts(tmem_d, tmem_gamma + (uint32_t)((h * KBS + kb) * 32 + ks * 8), dB + advB, idescA, accumulate);
+                                else mma_tf32(tmem_d, descGA + advG, dB + advB, idescA, accumulate);
+                                if (Cfg::kTwoBlocks) mma_tf32(tmem_d + kColsB, descGB + advG, dB + advB, idescB, accumulate);
+                            }
                         }
                     }
+                    mma_commit(bar_empty + 8 * s);   // shared-memory stage free once these MMAs have read it
+                    if (h == KS - 1) mma_commit(bar_tfull + 8 * a);   // accumulator complete
                 }
-                mma_commit(bar_empty + 8 * s);       // shared-memory stage free once these MMAs have read it
-                mma_commit(bar_tfull + 8 * a);       // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
     fence_before_sync();
     __syncthreads();
     if (warp == kEpiWarps + kProdWarps) {
         fence_after_sync();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(2 * kAccCols));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
+}
+
+// SIC_DENSE_PREFETCH=0 switches the bulk L2 prefetch off (A/B timing only; results are identical either way)
+inline int dense_prefetch_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SIC_DENSE_PREFETCH");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
+// SIC_DENSE_TS=1: gamma as a tensor-memory A operand (experimental until parity-tested on the device); default: shared memory
+inline int dense_gamma_in_tmem() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SIC_DENSE_TS");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
 }
 
 template <int C>
@@ -305,7 +371,7 @@ int launch_dense_ws(const float *x, const float *beta_param, const float *gamma_
     }
     const long n_tiles = (P + WsCfg<C>::TN - 1) / WsCfg<C>::TN;
     const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());   // persistent: one CTA per SM
-    kern<<<grid, kThreadsWS, smem, st>>>(x, beta_param, gamma_param, P, y);
+    kern<<<grid, kThreadsWS, smem, st>>>(x, beta_param, gamma_param, P, dense_prefetch_enabled(), dense_gamma_in_tmem(), y);
     SIC_CHECK_LAUNCH("sic_gdn_dense_fwd (pipelined)");
     return 0;
 }
