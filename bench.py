@@ -10,7 +10,8 @@ one flat-bucket NCCL all-reduce per step for N > 1.  Prints ONE JSON line (rank 
   value     patches/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e       same metric through the public API with the batch coming from pinned HOST memory every step and the loss read
             back to the host every step
-  roofline  dominant own kernel (GDN backward): algorithmic bytes / CUDA-event time, measured in this run
+  roofline  dominant own kernel of the step (GDN backward in the step's layout): algorithmic bytes / CUDA-event time,
+            measured in this run
   cpu_baseline  the reference's eager op chains (oracle/torch_port.py — /root/reference itself cannot travel to the GPU box)
             on the host cores, bounded sample
 --impl reference: only the CPU arm (rank 0), same metric/config/unit.
@@ -177,7 +178,7 @@ def run_ours(args):
     cfg = CONFIGS[args.config]
     B, H, W = cfg["batch"], cfg["H"], cfg["W"]
     # kernel rooflines first: they draw from torch's CUDA generator, which must not be touched between graph replays
-    roof, kernels = kernel_rooflines(cfg, dev) if rank == 0 else (None, None)
+    roof, kernels = kernel_rooflines(cfg, dev, channels_last=not args.nchw) if rank == 0 else (None, None)
     if world > 1:
         dist.barrier()
     torch.manual_seed(42)                                      # config.py:32
@@ -294,7 +295,7 @@ def run_ours(args):
         os._exit(0)
 
 
-def kernel_rooflines(cfg, dev):
+def kernel_rooflines(cfg, dev, channels_last=True):
     """CUDA-event timing of our own kernels at the sizes they have inside the step (largest GDN site, the latent), inputs
     larger than L2 or L2 flushed in between.  achieved = algorithmic bytes / time (GDN fwd 8 B/elem,
     bwd 12 B/elem; K1 fwd 12 B/elem broadcast, bwd 8 B/elem + 4 for the dense upstream of y_tilde)."""
@@ -354,15 +355,31 @@ def kernel_rooflines(cfg, dev):
         ne = yl.numel()
         out[tag] = {"shape": list(shape), "bytes": 12 * ne, "ms": t * 1e3, "gbs": 12 * ne / t / 1e9}
         del yl
+    # G3 (north_star's tensor-core contraction; not on the default step, which runs the reference's diagonal GDN): pipelined
+    # tcgen05 kernel at the same site shape
+    if N in (32, 64, 96, 128, 192):
+        xd = torch.randn(B if N <= 128 else max(B // 2, 1), N, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
+        gm = torch.sqrt(torch.rand(N, N, device=dev) * 0.02 + torch.eye(N, device=dev) * 0.1 + 2.0 ** -18)
+        bd = torch.sqrt(torch.rand(N, device=dev) + 0.5)
+        t = time_it(lambda: F.gdn_dense(xd, bd, gm, False))
+        nd = xd.numel()
+        out["gdn_dense_fwd_tcgen05"] = {"shape": list(xd.shape), "bytes": 8 * nd, "ms": t * 1e3, "gbs": 8 * nd / t / 1e9,
+                                        "tf32_mma_tflops": 4.0 * N * nd / t / 1e12}
+        del xd
     for v in out.values():
         v["frac_of_hbm_peak"] = v["gbs"] / peak
-    dom = out["gdn_bwd"]
-    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed ncu --set full capture
-    # (profiles/r01a_ncu_k1_gdn_first_version.txt: 1073.8 MB read + 498.1 MB written; the kernel's memory access pattern has
-    # not changed since).  Only meaningful for the cfg2 site shape.
-    traffic = 1.0737e9 + 0.4981e9 if (B, N) == (16, 128) else None
-    roof = {"kernel": "gdn_bwd_kernel (GDN backward) at the largest site of the step", "bound": "hbm", "achieved": dom["gbs"], "peak": peak,
-            "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01a_ncu_k1_gdn_first_version.txt",
+    # The dominant own kernel of the step is the GDN backward at the largest site, in the layout the step actually runs
+    # (channels_last by default -> gdn_bwd_nhwc_kernel; --nchw -> gdn_bwd_kernel).  `traffic` = dram__bytes_read.sum +
+    # dram__bytes_write.sum of that kernel at this shape from the committed ncu --set full capture
+    # (profiles/r01_ncu_kernels_final.txt); only meaningful for the cfg2 site shape.
+    if channels_last:
+        dom, kname = out["gdn_bwd_channels_last"], "gdn_bwd_nhwc_kernel (GDN backward, channels_last) at the largest site of the step"
+        traffic = 1.073845e9 + 0.501128e9 if (B, N) == (16, 128) else None
+    else:
+        dom, kname = out["gdn_bwd"], "gdn_bwd_kernel (GDN backward, NCHW) at the largest site of the step"
+        traffic = 1.0737e9 + 0.4981e9 if (B, N) == (16, 128) else None
+    roof = {"kernel": kname, "bound": "hbm", "achieved": dom["gbs"], "peak": peak,
+            "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01_ncu_kernels_final.txt",
             "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"]}
     return roof, out
 

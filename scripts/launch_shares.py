@@ -11,8 +11,8 @@ for r in rows:
 ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 agg, tot = collections.defaultdict(lambda: [0, 0.0]), 0.0
 for r in data:
-    full = r[ik]
-    ours = "sic::" in full or re.search(r"(bottleneck_(fwd|bwd)_kernel|gdn_(fwd|bwd|dense)|cdf_tables_kernel|minmax|symbols_kernel)", full)
+    full = r[ik].replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+    ours = "sic::" in r[ik] or re.search(r"(bottleneck_(fwd|bwd)_kernel|gdn_(fwd|bwd|dense)|cdf_tables_kernel|minmax|symbols_kernel)", full)
     name = re.sub(r"<.*", "", re.sub(r"\(.*", "", full)).split("::")[-1].replace("void ", "")[:58]
     key = ("[sic] " if ours else "      ") + name
     v = float(r[iv].replace(",", "")) / (1000.0 if r[iu] == "ns" else 1.0)

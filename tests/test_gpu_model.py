@@ -167,3 +167,32 @@ def test_stream_erasure_is_detected(golden):
     comp["strings"][0][1] = comp["strings"][0][1][:-6]
     with pytest.raises(sic.SicError):
         m.decompress(comp)
+
+
+@pytest.mark.parametrize("N", [128, 192])
+def test_model_with_dense_gamma_gdn_on_tensor_cores(N):
+    """north_star's G3 inside the model: every GDN/IGDN site switched to the dense C x C gamma (tcgen05 kernel, C = N).  With the
+    reference's initialisation (layers.py:13) gamma is diagonal, so the dense model must reproduce the reference-path model
+    up to gamma at TF32 precision; gradients flow to the C x C matrices instead of the depthwise weights."""
+    import domain_specific_image_compression_b200 as sic
+    torch.manual_seed(N)
+    m = sic.CompressionModel(N=N, M=64, spatial_params=False, min_nu=2.0, max_nu=100.0).cuda()
+    with torch.no_grad():
+        m.g_a.g_a[14].weight.mul_(20.0)             # spread the latents (default init gives y ~ 0: SURVEY 8(d))
+    x = torch.rand(2, 3, 64, 64, device="cuda")
+    noise_y = torch.rand(2, 64, 4, 4, device="cuda") - 0.5
+    noise_z = torch.rand(2, N, 1, 1, device="cuda") - 0.5
+    ref = m(x, "noise", noise_y=noise_y, noise_z=noise_z)
+    sites = [mod for mod in m.modules() if isinstance(mod, sic.GDN)]
+    assert len(sites) == 13
+    for mod in sites:
+        mod.dense = True
+    out = m(x, "noise", noise_y=noise_y, noise_z=noise_z)
+    for k in ("y", "x_hat"):
+        a, b = out[k], ref[k]
+        assert float((a - b).abs().max()) <= 5e-3 * float(b.abs().max()) + 1e-6, k
+    loss, _, _ = sic.rate_distortion_loss(out, x, lambda_rd=100.0, dist="mse")
+    loss.backward()
+    for mod in sites:
+        assert mod.gamma.grad is not None and torch.isfinite(mod.gamma.grad).all() and float(mod.gamma.grad.abs().max()) > 0
+        assert mod.gamma_conv.weight.grad is None
