@@ -1,0 +1,135 @@
+"""Patch-parallel compress/decompress (rank r codes patches r, r+W, ...; host gather, no data-path collective).
+CPU part: the sharding / merge logic over real `gloo` process groups with a stand-in codec (the product codec is CUDA only).
+GPU part: the real model, shards merged in-process, round trip against forward()."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from domain_specific_image_compression_b200 import codec_parallel as CP
+
+
+class FakeCodec:
+    """compress(): per-patch byte strings derived from the patch content; decompress(): inverts them.  Same dict layout as
+    CompressionModel.compress (custom_compress, eval_selfcontained_entropy.py:68-74)."""
+
+    def compress(self, x, tail=10, coder="gpu"):
+        B = x.size(0)
+        q = (x * 255).round().to(torch.uint8)
+        return {"strings": [[q[b, :1].numpy().tobytes(), q[b].numpy().tobytes()] for b in range(B)],
+                "shape_y": [B, 3, x.size(2), x.size(3)], "shape_z": [B, 1, x.size(2), x.size(3)],
+                "min_y": [int(q[b].min()) - tail for b in range(B)], "max_y": [int(q[b].max()) + tail for b in range(B)],
+                "min_z": [int(q[b, :1].min()) - tail for b in range(B)], "max_z": [int(q[b, :1].max()) + tail for b in range(B)]}
+
+    def decompress(self, compressed, coder="gpu"):
+        B = len(compressed["strings"])
+        shp = compressed["shape_y"][1:]
+        out = torch.empty(B, *shp)
+        for b in range(B):
+            out[b] = torch.from_numpy(np.frombuffer(compressed["strings"][b][1], np.uint8).reshape(shp).copy()).float() / 255
+        return out
+
+
+def _batch(n):
+    return torch.rand(n, 3, 4, 5, generator=torch.Generator().manual_seed(n))
+
+
+def test_patch_indices_cover_every_patch_once():
+    for n in (0, 1, 5, 8):
+        for w in (1, 2, 3, 8):
+            got = sorted(i for r in range(w) for i in CP.patch_indices(n, r, w))
+            assert got == list(range(n))
+    with pytest.raises(ValueError):
+        CP.patch_indices(4, 2, 2)
+
+
+@pytest.mark.parametrize("n,world", [(5, 2), (2, 3), (6, 3), (1, 1)])
+def test_merge_of_shards_equals_single_process(n, world):
+    codec, x = FakeCodec(), _batch(n)
+    whole = codec.compress(x)
+    parts = [CP.compress_sharded(codec, x, gather=False, rank=r, world=world) for r in range(world)]
+    merged = CP.merge_compressed(parts, n)
+    assert merged == whole
+    for r in range(world):
+        idx = CP.patch_indices(n, r, world)
+        assert CP.split_compressed(merged, idx) == (parts[r][1] if idx else {**{k: [] for k in CP._PER_PATCH_KEYS},
+                                                                           "shape_y": [0, 3, 4, 5], "shape_z": [0, 1, 4, 5]})
+
+
+def test_merge_detects_missing_and_duplicate_patches():
+    codec, x = FakeCodec(), _batch(4)
+    p0 = CP.compress_sharded(codec, x, gather=False, rank=0, world=2)
+    with pytest.raises(ValueError, match="not produced"):
+        CP.merge_compressed([p0], 4)
+    with pytest.raises(ValueError, match="twice"):
+        CP.merge_compressed([p0, p0], 4)
+    with pytest.raises(ValueError, match="does not match"):
+        CP.merge_compressed([(p0[0], None)], 4)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    codec, x = FakeCodec(), _batch(n)
+    merged = CP.compress_sharded(codec, x)                       # rank/world from the process group, host gather
+    x_hat = CP.decompress_sharded(codec, merged)
+    q.put((rank, merged, x_hat.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,world", [(5, 2), (2, 3)])
+def test_gloo_ranks_gather_the_single_process_result(n, world):
+    """world_size 2 with a ragged split, world_size 3 with an idle rank: every rank ends with the single-process dict and
+    the full reconstruction, in patch order."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    codec, x = FakeCodec(), _batch(n)
+    whole = codec.compress(x)
+    want = codec.decompress(whole).numpy()
+    assert sorted(r for r, _, _ in got) == list(range(world))
+    for _, merged, x_hat in got:
+        assert merged == whole
+        np.testing.assert_array_equal(x_hat, want)
+
+
+@pytest.mark.gpu
+def test_sharded_round_trip_on_the_real_model():
+    """Two shards coded by the real CUDA path and merged in-process; each shard's reconstruction equals the forward pass of
+    that shard bit for bit (the same property tests/test_gpu_model.py checks for a whole batch)."""
+    import domain_specific_image_compression_b200 as sic
+    torch.manual_seed(5)
+    m = sic.CompressionModel(N=16, M=24, spatial_params=False, min_nu=2.0, max_nu=100.0).cuda().eval()
+    with torch.no_grad():
+        m.g_a.g_a[14].weight.mul_(30.0)
+        m.h_a.h_a[6].weight.mul_(30.0)
+    x = torch.rand(5, 3, 64, 64, device="cuda")
+    world = 2
+    parts = [CP.compress_sharded(m, x, gather=False, rank=r, world=world) for r in range(world)]
+    merged = CP.merge_compressed(parts, 5)
+    assert len(merged["strings"]) == 5 and merged["shape_y"][0] == 5
+    for r in range(world):
+        idx, x_hat = CP.decompress_sharded(m, merged, gather=False, rank=r, world=world)
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True):
+            want = m(x[idx], quant_mode="round")["x_hat"].clamp(0, 1)
+        assert torch.equal(x_hat, want)
