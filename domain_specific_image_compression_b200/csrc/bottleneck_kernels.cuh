@@ -430,14 +430,20 @@ __device__ __forceinline__ TBwdConst t_bwd_const(float sigma_raw, float nu_raw) 
     c.inv_nu = 1.0f / n;
     c.mask_s = (sigma_raw >= kSigmaMin && sigma_raw <= kSigmaMax) ? 1.0f : 0.0f;  // torch.clamp passes grad on the closed interval
     c.mask_n = (nu_raw >= kNuMin && nu_raw <= kNuMax) ? 1.0f : 0.0f;
-    // Knu = 0.5*(psi((nu+1)/2) - psi(nu/2)) - 1/(2 nu)
-    double a = 0.5 * (double)n, b = a + 4.0, rb = 1.0 / b, rb2 = rb * rb;
-    double E = rb * (0.5 + rb * (0.125 + rb2 * (-0.015625 + rb2 * 0.0078125)));
-    E += 1.0 / a - 1.0 / (a + 0.5);
-    E += 1.0 / (a + 1.0) - 1.0 / (a + 1.5);
-    E += 1.0 / (a + 2.0) - 1.0 / (a + 2.5);
-    E += 1.0 / (a + 3.0) - 1.0 / (a + 3.5);
-    c.Knu = (float)(0.5 * E - 0.25 / a);
+    // Knu = 0.5*(psi((nu+1)/2) - psi(nu/2)) - 1/(2 nu)  ~ 1/(4 nu^2): the three terms cancel to 1e-4 of their size, which is why
+    // this used to be a binary64 chain (12 DDIVs per lane per unit, and per ELEMENT in the spatial layout).  Shifting
+    // a = nu/2 by 4 with the psi recurrence and telescoping 1/(4a) the same way leaves a sum of POSITIVE terms that float32
+    // carries to 4e-7 relative (checked against scipy digamma over nu in [2,100]):
+    //   Knu = sum_{k<4} (1/8) / ((a+k)(a+k+1/2)(a+k+1))  +  rb^2 (1/16 - rb^2/128 + rb^4/256),   rb = 1/(a+4)
+    const float a = 0.5f * n;
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float ak = a + (float)k;
+        acc += __fdividef(0.125f, ak * (ak + 0.5f) * (ak + 1.0f));
+    }
+    const float rb = __fdividef(1.0f, a + 4.0f), rb2 = rb * rb;
+    c.Knu = acc + rb2 * (0.0625f + rb2 * (-0.0078125f + rb2 * 0.00390625f));
     return c;
 }
 

@@ -192,13 +192,13 @@ class _GDN(torch.autograd.Function):
         B, C = x.shape[0], x.shape[1]
         if beta_param.numel() != C or gamma_weight.numel() != C:
             raise _lib.SicError(f"GDN parameters have {beta_param.numel()}/{gamma_weight.numel()} entries for {C} channels")
+        if bias is not None and bias.numel() != C:   # before the launch: the kernel indexes bias[c]
+            raise _lib.SicError(f"bias has {bias.numel()} entries for {C} channels")
         HW = x.numel() // (B * C)
         y = torch.empty_like(x)                       # keeps x's memory format (NCHW or channels_last)
         with torch.cuda.device(x.device):
             _launch(lib.sic_gdn_fwd(_ptr(x), _ptr(bias), _ptr(beta_param), _ptr(gamma_weight), B, C, HW, int(inverse), cl, _ptr(y),
                                     _stream()), "sic_gdn_fwd")
-        if bias is not None and bias.numel() != C:
-            raise _lib.SicError(f"bias has {bias.numel()} entries for {C} channels")
         ctx.save_for_backward(x, beta_param, gamma_weight, bias)
         ctx.cfg = (B, C, HW, int(inverse), cl)
         return y.contiguous(memory_format=torch.channels_last) if back_to_cl else y
@@ -348,6 +348,8 @@ def quantize_indices(q: torch.Tensor, do_round: bool = False, tail: int = 10, wa
     lib = _lib.load()
     q = _require_cuda_f32(q, "q")
     B = q.shape[0]
+    if q.numel() == 0:
+        raise _lib.SicError("quantize_indices: empty latent (no patches or no elements) has no support")
     n_per = q.numel() // B
     sym = torch.empty(q.shape, dtype=torch.int32, device=q.device) if want_symbols else None
     mins = torch.empty(B, dtype=torch.int32, device=q.device)
