@@ -267,9 +267,12 @@ def run_ours(args):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, ms, cores = cpu_reference(cfg, 1, 1, 4, args.dist)
+        # bounded sample (~10 s of CPU work on the box's cores): 3 timed steps of 8 patches (BASELINE.json configs[0] runs the
+        # CPU case at batch 8) after 1 warm-up step; cfg4's model is 2.3x the work per patch, so it gets 4 patches
+        cb = 8 if cfg["N"] <= 128 else 4
+        v, ms, cores = cpu_reference(cfg, 3, 1, cb, args.dist)
         cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"1 step of 4 patches (after 1 warm-up step) of the {args.config} training step, oracle/torch_port.py eager fp32"}
+                    "sample": f"3 steps of {cb} patches (after 1 warm-up step) of the {args.config} training step, oracle/torch_port.py eager fp32"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms_total / K,
