@@ -34,6 +34,8 @@ PROTOTYPES = {
     "sic_gdn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "sic_gdn_dense_fwd": (_i, [_p, _p, _p, _l, _i, _i, _p, _p]),
     "sic_gdn_dense_fwd_variant": (_i, [_p, _p, _p, _l, _i, _i, _p, _i, _p]),
+    "sic_gdn_dense_bwd_part_rows": (_i, [_l, _i]),
+    "sic_gdn_dense_bwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _i, _p]),
     "sic_ssim_tiles": (_l, [_i, _i]),
     "sic_ssim_fwd": (_i, [_p, _p, _i, _i, _i, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p]),
     "sic_ssim_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),

@@ -29,6 +29,7 @@ SOURCES = [
     ("gdn.cu", []),
     ("gdn_dense.cu", []),
     ("gdn_dense_ws.cu", []),
+    ("gdn_dense_bwd.cu", []),
     ("msssim.cu", []),
     ("tables.cu", ["-fmad=false"]),
     ("rans_host.cpp", []),

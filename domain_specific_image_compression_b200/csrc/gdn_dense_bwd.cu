@@ -1,28 +1,20 @@
-// G3, pipelined version: dense-gamma GDN / IGDN on tcgen05 with warp-specialised producer / MMA / epilogue roles.
+// G3 backward: dense-gamma GDN / IGDN gradients on the pipelined tcgen05 kernel of gdn_dense_ws.cu (SURVEY.md 8(a') G3).
 //
-//   s[p,i] = beta_i + sum_j gamma_ij * x[p,j]^2 ,   y = x / sqrt(s)   (IGDN: x * sqrt(s))        (layers.py:13,19-27)
+//   s_i = beta_i + sum_j gamma_ij x_j^2,  d = sqrt(s)
+//   GDN :  h_i = -1/2 g_i x_i / d_i^3,  dx_j = g_j / d_j + 2 x_j sum_i gamma_ij h_i
+//   IGDN:  h_i = +1/2 g_i x_i / d_i,    dx_j = g_j d_j  + 2 x_j sum_i gamma_ij h_i
+//   d(beta_eff)_i = sum_p h_i ,  d(gamma_eff)_ij = sum_p h_i x_j^2   (the latter stays a library GEMM on the emitted h)
 //
-// gdn_dense.cu runs load -> square -> MMA -> epilogue strictly one after the other on every tile (48 % of the HBM peak).  Here
-// the three phases of consecutive tiles overlap:
+// Two launches of the same warp-specialised producer / MMA / epilogue pipeline as the forward (identical barriers, descriptors,
+// stage ring and TMEM layout; only the producer's pre-op, the orientation of gamma and the epilogue differ):
+//   pass 1  MMA as in the forward (s); epilogue emits h and direct = g/d | g d and accumulates sum_p h per lane (= per channel)
+//   pass 2  gamma TRANSPOSED into the A operand, h split hi/lo as the B operand (t = gamma^T h); epilogue dx = direct + 2 x t
+// Algorithmic traffic: pass 1 reads x, g and writes h, direct; pass 2 reads h, x, direct and writes dx: 32 B/element, against
+// ~100 B/element for the elementwise + cuBLAS chain through torch that it replaces.
 //
-//   producer warps (8)   x tile (TN positions x C, one contiguous block of channels-last memory) -> registers (requested one
-//                        tile ahead) -> x^2 split exactly into tf32 hi + lo -> shared memory in the K-major SWIZZLE_128B UMMA
-//                        layout -> mbarrier full[s]
-//   MMA warp (1 thread)  D[c_out, pos] (TMEM, 2 accumulator stages) = G[c_out, c_in] (smem, resident) * X2[pos, c_in]^T,
-//                        2 * C/8 tcgen05.mma kind::tf32 per M block; tcgen05.commit -> empty[s] and tmem_full[a]
-//   epilogue warps (8)   tcgen05.ld: lane = output channel, columns = positions.  With channels-last activations the lanes of a
-//                        warp therefore address CONSECUTIVE floats for any fixed position: x is re-read (an L2 hit: the producer
-//                        touched the tile microseconds earlier with a normal-priority load) and y = x * rsqrt(beta + acc) is
-//                        written with coalesced warp accesses and no shared-memory transpose -> mbarrier tmem_empty[a]
-//
-// gamma is the A operand (M = output channels), the x^2 tile is the B operand (N = positions).  That orientation is what removes
-// the transpose of the first version (its TMEM lanes were positions, so a thread held 32 channels of ONE position and had to go
-// through padded shared memory to store coalesced).
-//   C <= 128: one M = 128 block (rows >= C zero-padded), TN = 128 positions per tile.
-//   C == 192: gamma (144 KB) still fits beside one x^2 stage when TN = 48: an M = 128 block (channels 0..127) plus an M = 64
-//             block (channels 128..191; its accumulator rows live in lanes 32*(j/16) + j%16, i.e. the low half of each warp's
-//             TMEM quadrant).  This covers the N = 192 model of BASELINE.json configs[3].
-// HBM traffic stays at the algorithmic 8 B/element; the epilogue's second read of x is L2 traffic (ncu: profiles/).
+// STATUS: written after the round's GPU budget was spent — compiled for sm_100a, NOT yet run on a device.  It is therefore opt-in
+// (SIC_DENSE_BWD=1 on the Python side); the default backward remains the torch/cuBLAS path.  The forward kernel in
+// gdn_dense_ws.cu is untouched (its SASS is byte-identical to the build the GPU tests validated).
 #include "gdn_dense_ws.cuh"
 
 namespace sic {
@@ -31,56 +23,114 @@ namespace {
 using namespace umma;
 using namespace dense_ws;
 
+// What the pipeline computes.  The producer / MMA / barrier machinery is the same for all five; they differ in the producer's
+// pre-op, in the orientation of gamma and in the epilogue:
+//   OP_FWD / OP_FWD_INV    s = beta + gamma x^2 ;  y = x / sqrt(s)  |  x sqrt(s)
+//   OP_BWD1 / OP_BWD1_INV  the same s, then (SURVEY 8(a') G3)  GDN:  direct = g / d,  h = -1/2 g x / d^3
+//                                                             IGDN: direct = g d,    h = +1/2 g x / d      ; also sum_p h per channel
+//   OP_BWD2                t = gamma^T h  (gamma transposed into the A operand, h split hi/lo like x^2) ;  dx = direct + 2 x t
+enum { OP_FWD = 0, OP_FWD_INV = 1, OP_BWD1 = 2, OP_BWD1_INV = 3, OP_BWD2 = 4 };   // only the OP_BWD* ones are instantiated here
+template <int OP>
+struct OpTraits {
+    static constexpr bool kInverse = OP == OP_FWD_INV || OP == OP_BWD1_INV;
+    static constexpr bool kFwd = OP == OP_FWD || OP == OP_FWD_INV;
+    static constexpr bool kBwd1 = OP == OP_BWD1 || OP == OP_BWD1_INV;
+    static constexpr bool kBwd2 = OP == OP_BWD2;
+};
+
+// epilogue tensors:  forward a = x, o0 = y;   pass 1: a = x, b = g, o0 = h, o1 = direct;   pass 2: a = x, b = direct, o0 = dx
+struct EpiPtrs {
+    const float *a, *b;
+    float *o0, *o1;
+};
+
 // Epilogue of one warp for one tile: NP positions of this lane's output channel (block A), then of its block-B channel when
-// C = 192.  x is fetched in batches of 16 positions through a 2-deep register ring: the first two batches are requested before
-// the accumulator barrier is awaited (their L2 latency hides behind the MMA), every later batch while the two before it are being
-// normalised and stored.  32 + 16 live values keep the role inside the 96-register budget of a 17-warp CTA without spills
-// (spill traffic shares the L1 data pipe with the tensor core's operand reads, which is this kernel's critical resource).
-template <int C, bool INVERSE, bool FULL>
-__device__ __forceinline__ void epilogue_tile(const float *__restrict__ x, float *__restrict__ y, long p0, int left, int cA, bool okA,
-                                              float betaA, int cB, bool okB, float betaB, uint32_t taddr, uint32_t bar,
-                                              uint32_t parity) {
+// C = 192.  The inputs are fetched in batches of 16 positions through a 2-deep register ring: the first two batches are requested
+// before the accumulator barrier is awaited (their L2 latency hides behind the MMA), every later batch while the two before it
+// are being processed and stored.  In the forward, 32 + 16 live values keep the role inside the 96-register budget of a 17-warp
+// CTA without spills (spill traffic shares the L1 data pipe with the tensor core's operand reads, this kernel's critical resource).
+template <int C, int OP, bool FULL>
+__device__ __forceinline__ void epilogue_tile(const EpiPtrs &p, long p0, int left, int cA, bool okA, float betaA, int cB, bool okB,
+                                              float betaB, uint32_t taddr, uint32_t bar, uint32_t parity, float &sumA, float &sumB) {
     using Cfg = WsCfg<C>;
+    using T = OpTraits<OP>;
     constexpr int NP = Cfg::NP;
     static_assert(NP % 16 == 0, "epilogue batches are 16 columns");
     constexpr int NBB = NP / 16;                                 // batches per block
     constexpr int NB = Cfg::kTwoBlocks ? 2 * NBB : NBB;
-    const float *xA = x + p0 * C + cA, *xB = x + p0 * C + cB;
-    float *yA = y + p0 * C + cA, *yB = y + p0 * C + cB;
+    const long offA = p0 * C + cA, offB = p0 * C + cB;
     float ring[2][16];
-    auto load = [&](float (&dst)[16], int b) {
+    float ring2[T::kFwd ? 1 : 2][T::kFwd ? 1 : 16];              // second input (g or direct) of the backward passes
+    auto load = [&](int slot, int b) {
         const bool blkB = b >= NBB;
         const int k0 = (blkB ? b - NBB : b) * 16;
-        const float *src = blkB ? xB : xA;
+        const long off = blkB ? offB : offA;
         const bool ok = blkB ? okB : okA;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dst[j] = (ok && (FULL || k0 + j < left)) ? __ldcg(src + (long)(k0 + j) * C) : 0.f;
+        for (int j = 0; j < 16; ++j) ring[slot][j] = (ok && (FULL || k0 + j < left)) ? __ldcg(p.a + off + (long)(k0 + j) * C) : 0.f;
+        if constexpr (!T::kFwd) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ring2[slot][j] = (ok && (FULL || k0 + j < left)) ? __ldcg(p.b + off + (long)(k0 + j) * C) : 0.f;
+        }
     };
-    load(ring[0], 0);
-    if (NB > 1) load(ring[1], 1);
+    load(0, 0);
+    if (NB > 1) load(1, 1);
     mbar_wait(bar, parity);
     fence_after_sync();
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const bool blkB = b >= NBB;
         const int k0 = (blkB ? b - NBB : b) * 16;
-        float *dst = blkB ? yB : yA;
+        const long off = blkB ? offB : offA;
         const bool ok = blkB ? okB : okA;
         const float beta = blkB ? betaB : betaA;
         float acc[16];
         tmem_ld16(taddr + (blkB ? kColsB : 0) + k0, acc);
+        float hsum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (ok && (FULL || k0 + j < left)) __stcs(dst + (long)(k0 + j) * C, ring[b & 1][j] * norm_factor<INVERSE>(beta + acc[j]));
-        if (b + 2 < NB) load(ring[b & 1], b + 2);
+        for (int j = 0; j < 16; ++j) {
+            if (ok && (FULL || k0 + j < left)) {
+                const long e = off + (long)(k0 + j) * C;
+                const float xv = ring[b & 1][j];
+                if constexpr (T::kFwd) {
+                    __stcs(p.o0 + e, xv * norm_factor<T::kInverse>(beta + acc[j]));
+                } else if constexpr (T::kBwd1) {
+                    const float gv = ring2[b & 1][j];
+                    const float s = beta + acc[j];
+                    const float r = norm_factor<false>(s);        // 1/sqrt(s)
+                    float direct, h;
+                    if (T::kInverse) {
+                        direct = gv * (s * r);                   // g d
+                        h = 0.5f * gv * xv * r;                  // 1/2 g x / d
+                    } else {
+                        direct = gv * r;                         // g / d
+                        h = -0.5f * direct * xv * (r * r);       // -1/2 g x / d^3
+                    }
+                    __stcs(p.o0 + e, h);
+                    __stcs(p.o1 + e, direct);
+                    hsum += h;
+                } else {
+                    __stcs(p.o0 + e, fmaf(2.0f * xv, acc[j], ring2[b & 1][j]));   // dx = direct + 2 x t
+                }
+            }
+        }
+        if constexpr (T::kBwd1) {
+            if (blkB) sumB += hsum;
+            else sumA += hsum;
+        }
+        if (b + 2 < NB) load(b & 1, b + 2);
     }
 }
 
-template <int C, bool INVERSE>
-__global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float *__restrict__ x, const float *__restrict__ beta_param,
+// in0: the tensor the producers feed to the MMA (x; h in pass 2).  out0 / in1 / in2 / out1 / part: see EpiPtrs and OP_*.
+template <int C, int OP>
+__global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float *__restrict__ in0, const float *__restrict__ beta_param,
                                                                      const float *__restrict__ gamma_param, long P, int use_prefetch,
-                                                                     int gamma_in_tmem, float *__restrict__ y) {
+                                                                     int gamma_in_tmem, float *__restrict__ out0,
+                                                                     const float *__restrict__ in1, const float *__restrict__ in2,
+                                                                     float *__restrict__ out1, float *__restrict__ part) {
     using Cfg = WsCfg<C>;
+    using T = OpTraits<OP>;
     constexpr int V = C / 4;                         // float4 per position
     constexpr int TN = Cfg::TN, NS = Cfg::NS, ROWS_G = Cfg::ROWS_G, NP = Cfg::NP, KS = Cfg::KS, KBS = Cfg::KBS;
     constexpr int VH = Cfg::VH, PER = Cfg::PER, ACC_COLS = Cfg::ACC_COLS;
@@ -100,7 +150,12 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
         const int i = idx / V, c4 = idx - i * V;
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < C) {
-            g = __ldg(reinterpret_cast<const float4 *>(gamma_param) + (size_t)i * V + c4);
+            if constexpr (T::kBwd2) {                // operand row i, K index k holds gamma[k][i]  (t_i = sum_k gamma_ki h_k)
+                const float *col = gamma_param + (size_t)(4 * c4) * C + i;
+                g = make_float4(__ldg(col), __ldg(col + C), __ldg(col + 2 * C), __ldg(col + 3 * C));
+            } else {
+                g = __ldg(reinterpret_cast<const float4 *>(gamma_param) + (size_t)i * V + c4);
+            }
             g.x = g.x * g.x - kReparamOffset; g.y = g.y * g.y - kReparamOffset;
             g.z = g.z * g.z - kReparamOffset; g.w = g.w * g.w - kReparamOffset;
         }
@@ -121,7 +176,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
     // tensor-memory-sourced MMA: the tensor core then reads only the x^2 tile from shared memory, which halves its share of the
     // L1/shared data pipe (ncu: that pipe, shared with the producers' stores and the epilogue's accesses, is the busiest unit)
     constexpr uint32_t TMEM_COLS = Cfg::kTwoBlocks ? 2 * ACC_COLS : 512;
-    const bool a_tmem = !Cfg::kTwoBlocks && gamma_in_tmem != 0;
+    const bool a_tmem = !Cfg::kTwoBlocks && !T::kBwd2 && gamma_in_tmem != 0;
     if (warp == kEpiWarps + kProdWarps) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
@@ -174,6 +229,12 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
             const float b = __ldg(beta_param + cB);
             betaB = b * b - kReparamOffset;
         }
+        EpiPtrs ep;
+        ep.a = T::kBwd2 ? in1 : in0;                 // x
+        ep.b = T::kBwd2 ? in2 : in1;                 // pass 1: g, pass 2: direct (unused in the forward)
+        ep.o0 = out0;
+        ep.o1 = out1;
+        float sumA = 0.f, sumB = 0.f;                // pass 1: sum over this warp's positions of h for the lane's channel(s)
         long it = 0;
         for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t a = (uint32_t)(it & 1), aph = (uint32_t)((it >> 1) & 1);
@@ -183,12 +244,17 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
             if (!okA || left <= 0) {
                 mbar_wait(bar_tfull + 8 * a, aph);
             } else if (left >= NP) {
-                epilogue_tile<C, INVERSE, true>(x, y, p0, NP, cA, okA, betaA, cB, okB, betaB, taddr, bar_tfull + 8 * a, aph);
+                epilogue_tile<C, OP, true>(ep, p0, NP, cA, okA, betaA, cB, okB, betaB, taddr, bar_tfull + 8 * a, aph, sumA, sumB);
             } else {
-                epilogue_tile<C, INVERSE, false>(x, y, p0, (int)left, cA, okA, betaA, cB, okB, betaB, taddr, bar_tfull + 8 * a, aph);
+                epilogue_tile<C, OP, false>(ep, p0, (int)left, cA, okA, betaA, cB, okB, betaB, taddr, bar_tfull + 8 * a, aph, sumA, sumB);
             }
             fence_before_sync();
             mbar_arrive(bar_tempty + 8 * a);         // accumulator stage a may be overwritten
+        }
+        if constexpr (T::kBwd1) {                    // d(beta_eff) partials: one row per (CTA, position half), folded by the caller
+            float *row = part + ((size_t)blockIdx.x * 2 + (size_t)(warp >> 2)) * C;
+            if (okA) row[cA] = sumA;
+            if (okB) row[cB] = sumB;
         }
     } else if (warp < kEpiWarps + kProdWarps) {
         // ===================================================== producer: x -> x^2 (hi, lo) -> smem, one K sub-step at a time
@@ -197,7 +263,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
         auto request = [&](long t, int h) {          // channels [h*32*KBS, (h+1)*32*KBS) of the TN positions of tile t -> registers
             const long q0 = t * TN;
             const long vld = P - q0;                 // <= 0 past the end
-            const float4 *src = reinterpret_cast<const float4 *>(x + q0 * C) + h * VH;
+            const float4 *src = reinterpret_cast<const float4 *>(in0 + q0 * C) + h * VH;
 #pragma unroll
             for (int k = 0; k < PER; ++k) {
                 const int idx = ptid + k * kProdThreads, r = idx / VH, c4 = idx - r * VH;
@@ -210,7 +276,9 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
             const long q0 = t * TN;
             if (use_prefetch && ptid == 0 && q0 < P) {
                 const long rows = (P - q0 < TN) ? (P - q0) : TN;
-                prefetch_l2_bulk(x + q0 * C, (uint32_t)(rows * C * 4));
+                prefetch_l2_bulk(in0 + q0 * C, (uint32_t)(rows * C * 4));
+                if constexpr (!T::kFwd) prefetch_l2_bulk(in1 + q0 * C, (uint32_t)(rows * C * 4));    // g (pass 1) / x (pass 2) for the epilogue
+                if constexpr (T::kBwd2) prefetch_l2_bulk(in2 + q0 * C, (uint32_t)(rows * C * 4));   // direct
             }
         };
         request(blockIdx.x, 0);
@@ -226,7 +294,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
                 for (int k = 0; k < PER; ++k) {
                     const int idx = ptid + k * kProdThreads, r = idx / VH, c4 = idx - r * VH;
                     const float4 v = xn[k];
-                    const float4 sq = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+                    const float4 sq = T::kBwd2 ? v : make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);   // pass 2 contracts h itself
                     float4 hi, lo;
                     hi.x = __uint_as_float(__float_as_uint(sq.x) & 0xFFFFE000u); lo.x = sq.x - hi.x;
                     hi.y = __uint_as_float(__float_as_uint(sq.y) & 0xFFFFE000u); lo.y = sq.y - hi.y;
@@ -295,37 +363,70 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
     }
 }
 
-template <int C>
-int launch_dense_ws(const float *x, const float *beta_param, const float *gamma_param, long P, int inverse, float *y, cudaStream_t st) {
+template <int C, int OP>
+int launch_dense_op(const char *what, const float *in0, const float *beta_param, const float *gamma_param, long P, float *out0,
+                    const float *in1, const float *in2, float *out1, float *part, cudaStream_t st) {
     const size_t smem = WsCfg<C>::SMEM;
-    auto kern = inverse ? gdn_dense_ws_kernel<C, true> : gdn_dense_ws_kernel<C, false>;
+    auto kern = gdn_dense_ws_kernel<C, OP>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
-        set_error("sic_gdn_dense_fwd (pipelined): cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+        set_error("%s: cannot reserve %zu B of shared memory: %s", what, smem, cudaGetErrorString(e));
         return (int)e;
     }
-    const long n_tiles = (P + WsCfg<C>::TN - 1) / WsCfg<C>::TN;
-    const int grid = (int)(n_tiles < sm_count() ? n_tiles : sm_count());   // persistent: one CTA per SM
-    kern<<<grid, kThreadsWS, smem, st>>>(x, beta_param, gamma_param, P, dense_prefetch_enabled(), dense_gamma_in_tmem(), y);
-    SIC_CHECK_LAUNCH("sic_gdn_dense_fwd (pipelined)");
+    kern<<<dense_grid(P, WsCfg<C>::TN), kThreadsWS, smem, st>>>(in0, beta_param, gamma_param, P, dense_prefetch_enabled(),
+                                                             dense_gamma_in_tmem(), out0, in1, in2, out1, part);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(le));
+        return (int)le;
+    }
     return 0;
+}
+
+// backward = pass 1 (s, h, direct, dbeta partials) then pass 2 (dx) on the same stream
+template <int C>
+int launch_dense_bwd(const float *x, const float *g, const float *beta_param, const float *gamma_param, long P, int inverse, float *h,
+                     float *direct, float *dx, float *dbeta_part, cudaStream_t st) {
+    const char *what = "sic_gdn_dense_bwd";
+    int rc = inverse ? launch_dense_op<C, OP_BWD1_INV>(what, x, beta_param, gamma_param, P, h, g, nullptr, direct, dbeta_part, st)
+                     : launch_dense_op<C, OP_BWD1>(what, x, beta_param, gamma_param, P, h, g, nullptr, direct, dbeta_part, st);
+    if (rc != 0) return rc;
+    return launch_dense_op<C, OP_BWD2>(what, h, beta_param, gamma_param, P, dx, x, direct, nullptr, nullptr, st);
 }
 
 }  // namespace
 
-int gdn_dense_ws_dispatch(const float *x, const float *beta_param, const float *gamma_param, long positions, int C, int inverse,
-                          float *y, cudaStream_t st) {
+static int dense_tile_positions(int C) { return C > 128 ? dense_ws::WsCfg<192>::TN : dense_ws::WsCfg<128>::TN; }
+
+}  // namespace sic
+
+using namespace sic;
+
+extern "C" int sic_gdn_dense_bwd_part_rows(long positions, int C) {
+    if (positions <= 0 || C <= 0) return 0;
+    return 2 * dense_ws::dense_grid(positions, dense_tile_positions(C));   // one row per (persistent CTA, position half)
+}
+
+extern "C" int sic_gdn_dense_bwd(const float *x, const float *g, const float *beta_param, const float *gamma_param, long positions,
+                                 int C, int inverse, float *h, float *direct, float *dx, float *dbeta_part, int part_rows,
+                                 void *stream) {
+    SIC_CHECK_ARG(positions > 0 && C > 0, "sic_gdn_dense_bwd: empty shape positions=%ld C=%d", positions, C);
+    SIC_CHECK_ARG(x && g && beta_param && gamma_param && h && direct && dx && dbeta_part, "sic_gdn_dense_bwd: null pointer");
+    SIC_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)g & 15) == 0 && ((uintptr_t)h & 15) == 0 && ((uintptr_t)direct & 15) == 0 &&
+                      ((uintptr_t)dx & 15) == 0 && ((uintptr_t)gamma_param & 15) == 0,
+                  "sic_gdn_dense_bwd: tensors must be 16-byte aligned");
+    SIC_CHECK_ARG(h != dx && direct != dx && h != direct, "sic_gdn_dense_bwd: h, direct and dx must be distinct buffers");
+    SIC_CHECK_ARG(part_rows >= sic_gdn_dense_bwd_part_rows(positions, C), "sic_gdn_dense_bwd: dbeta_part has %d rows, needs %d",
+                  part_rows, sic_gdn_dense_bwd_part_rows(positions, C));
+    cudaStream_t st = (cudaStream_t)stream;
     switch (C) {
-        case 32: return launch_dense_ws<32>(x, beta_param, gamma_param, positions, inverse, y, st);
-        case 64: return launch_dense_ws<64>(x, beta_param, gamma_param, positions, inverse, y, st);
-        case 96: return launch_dense_ws<96>(x, beta_param, gamma_param, positions, inverse, y, st);
-        case 128: return launch_dense_ws<128>(x, beta_param, gamma_param, positions, inverse, y, st);
-        case 192: return launch_dense_ws<192>(x, beta_param, gamma_param, positions, inverse, y, st);
+        case 32: return launch_dense_bwd<32>(x, g, beta_param, gamma_param, positions, inverse, h, direct, dx, dbeta_part, st);
+        case 64: return launch_dense_bwd<64>(x, g, beta_param, gamma_param, positions, inverse, h, direct, dx, dbeta_part, st);
+        case 96: return launch_dense_bwd<96>(x, g, beta_param, gamma_param, positions, inverse, h, direct, dx, dbeta_part, st);
+        case 128: return launch_dense_bwd<128>(x, g, beta_param, gamma_param, positions, inverse, h, direct, dx, dbeta_part, st);
+        case 192: return launch_dense_bwd<192>(x, g, beta_param, gamma_param, positions, inverse, h, direct, dx, dbeta_part, st);
         default:
-            set_error("sic_gdn_dense_fwd: C=%d unsupported (gamma and one x^2 hi/lo tile must be resident in shared memory: "
-                      "C in {32,64,96,128,192})", C);
+            set_error("sic_gdn_dense_bwd: C=%d unsupported (C in {32,64,96,128,192})", C);
             return SIC_E_UNSUPPORTED;
     }
 }
-
-}  // namespace sic

@@ -6,6 +6,7 @@ be CUDA float32 tensors — there is no CPU or eager fallback (the CPU oracle li
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -268,6 +269,8 @@ class _GDNDense(torch.autograd.Function):
     def backward(ctx, g):
         xc, beta_param, gamma_param = ctx.saved_tensors
         B, C, H, W = xc.shape
+        if os.environ.get("SIC_DENSE_BWD") == "1":
+            return _GDNDense._backward_fused(ctx, g, xc, beta_param, gamma_param)
         X = xc.permute(0, 2, 3, 1).reshape(-1, C)                    # [P, C] view of the channels-last block
         G = g.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(-1, C)
         beta = beta_param * beta_param - 2.0 ** -18
@@ -285,6 +288,29 @@ class _GDNDense(torch.autograd.Function):
         dgamma = h.t() @ X2                                          # dgamma_ij = sum_p h_i x2_j
         dbeta = h.sum(0)
         dx = dX.reshape(B, H, W, C).permute(0, 3, 1, 2)
+        return dx, dbeta * 2.0 * beta_param, dgamma * 2.0 * gamma_param, None, None
+
+
+    @staticmethod
+    def _backward_fused(ctx, g, xc, beta_param, gamma_param):
+        """Opt-in (SIC_DENSE_BWD=1): the two-pass tcgen05 backward of csrc/gdn_dense_bwd.cu — dx, h and the d(beta) partials come
+        from the kernels, d(gamma) = h^T x^2 stays a library GEMM.  Not device-tested yet (see include/sic.h)."""
+        lib = _lib.load()
+        B, C, H, W = xc.shape
+        P = B * H * W
+        gc = _dense_layout(g.contiguous(memory_format=torch.channels_last), "grad_output")[0]
+        h, direct, dx = torch.empty_like(xc), torch.empty_like(xc), torch.empty_like(xc)
+        rows = lib.sic_gdn_dense_bwd_part_rows(P, C)
+        part = torch.empty((rows, C), dtype=torch.float32, device=xc.device)
+        with torch.cuda.device(xc.device):
+            _lib.check(lib.sic_gdn_dense_bwd(_ptr(xc), _ptr(gc), _ptr(beta_param), _ptr(gamma_param), P, C, int(ctx.inverse), _ptr(h),
+                                             _ptr(direct), _ptr(dx), _ptr(part), rows, _stream()), "sic_gdn_dense_bwd")
+        global launch_count
+        launch_count += 2
+        X = xc.permute(0, 2, 3, 1).reshape(-1, C)
+        Hm = h.permute(0, 2, 3, 1).reshape(-1, C)
+        dgamma = Hm.t() @ (X * X)                                   # d(gamma_eff)_ij = sum_p h_i x_j^2
+        dbeta = part.sum(0)
         return dx, dbeta * 2.0 * beta_param, dgamma * 2.0 * gamma_param, None, None
 
 

@@ -113,6 +113,20 @@ enum { SIC_DENSE_SERIAL = 0, SIC_DENSE_PIPELINED = 1, SIC_DENSE_DEFAULT = SIC_DE
 int sic_gdn_dense_fwd_variant(const float *x, const float *beta_param, const float *gamma_param, long positions, int C,
                               int inverse, float *y, int variant, void *stream);
 
+/* G3 backward (SURVEY.md 8(a') G3) on the same pipelined tcgen05 kernel, two launches on `stream`:
+ *   pass 1: s = beta + gamma x^2 (MMA), h = -1/2 g x / d^3 | +1/2 g x / d, direct = g / d | g d, per-channel partial sums of h;
+ *   pass 2: t = gamma^T h (MMA, gamma transposed into the A operand), dx = direct + 2 x t.
+ *   x, g, h, direct, dx: channels-last [positions, C]; h and direct are caller-allocated outputs (h is also what the caller
+ *   contracts with x^2 for d(gamma_eff)_ij = sum_p h_i x_j^2, a plain library GEMM); dbeta_part [part_rows, C] with
+ *   part_rows >= sic_gdn_dense_bwd_part_rows(positions, C): d(beta_eff) = column sums.  Gradients are w.r.t. the EFFECTIVE
+ *   beta/gamma; the chain rule through the squared re-parameterisation (x 2 beta_param, x 2 gamma_param) is the caller's.
+ *   gamma is consumed at TF32 precision as in the forward.  C in {32, 64, 96, 128, 192}.
+ *   STATUS: compiled for sm_100a but not yet device-tested (written after the round's GPU budget was spent); the Python host
+ *   only uses it when SIC_DENSE_BWD=1. */
+int sic_gdn_dense_bwd_part_rows(long positions, int C);
+int sic_gdn_dense_bwd(const float *x, const float *g, const float *beta_param, const float *gamma_param, long positions, int C,
+                      int inverse, float *h, float *direct, float *dx, float *dbeta_part, int part_rows, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * K4  symbols: eval_selfcontained_entropy.py:39-40,48 / :52-53,62 (per patch, no host sync).
  *   q [B,n_per_patch] float latent; do_round != 0 applies torch.round first.

@@ -1,4 +1,6 @@
 """K2 (diagonal GDN / IGDN) on the GPU through the C ABI: forward bit-exact, backward within tolerance."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -289,3 +291,36 @@ def test_fused_conv_bias_is_bit_exact_and_returns_bias_gradient(fmt, inverse):
     for mine, ref in zip(ga, (xb.grad, beta.grad, w.grad, bias.grad)):
         assert float((mine - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-7
     assert float((ga[3] - ga[0].sum(dim=(0, 2, 3))).abs().max()) <= 1e-5 * float(ga[3].abs().max()) + 1e-6
+
+
+# ------------------------------------------------------------------------------ G3 backward on tcgen05 (opt-in, not yet device-tested)
+@pytest.mark.skipif(os.environ.get("SIC_EXPERIMENTAL") != "1",
+                    reason="csrc/gdn_dense_bwd.cu was written after the round's GPU budget ran out; run with SIC_EXPERIMENTAL=1 to validate it")
+@pytest.mark.parametrize("inverse", [False, True])
+@pytest.mark.parametrize("shape", [(2, 64, 9, 11), (1, 128, 24, 24), (2, 192, 10, 13), (1, 96, 5, 7), (1, 128, 148 * 3 + 1, 128)])
+def test_dense_gdn_fused_backward_vs_float64(shape, inverse, monkeypatch):
+    """Two-pass tcgen05 backward (sic_gdn_dense_bwd) against float64 autograd through F.conv2d(x^2, gamma, beta) with the
+    effective gamma truncated to TF32 (what both MMA passes consume).  dx tight; d(beta), d(gamma) through the same h."""
+    monkeypatch.setenv("SIC_DENSE_BWD", "1")
+    F = _F()
+    B, C, H, W = shape
+    gen = torch.Generator(device="cuda").manual_seed(C + H + inverse)
+    x = (torch.randn(shape, device="cuda", generator=gen) * 2).requires_grad_(True)
+    go = torch.randn(shape, device="cuda", generator=gen)
+    beta_p = torch.sqrt(torch.rand(C, device="cuda", generator=gen) + 0.5).requires_grad_(True)
+    gamma_p = torch.sqrt(torch.rand(C, C, device="cuda", generator=gen) * 0.02 + torch.eye(C, device="cuda") * 0.1 + 2.0 ** -18).requires_grad_(True)
+    y = F.gdn_dense(x, beta_p, gamma_p, inverse)
+    y.backward(go)
+    # float64 reference with gamma_eff at TF32 (a leaf, so its gradient is d/d gamma_eff)
+    xd = x.detach().double().requires_grad_(True)
+    be = (beta_p.detach() ** 2 - 2.0 ** -18).double().requires_grad_(True)
+    ge32 = gamma_p.detach() ** 2 - 2.0 ** -18
+    ge = (ge32.view(torch.int32) & -8192).view(torch.float32).double().requires_grad_(True)
+    s = torch.nn.functional.conv2d(xd * xd, ge.view(C, C, 1, 1), be)
+    yd = xd * torch.sqrt(s) if inverse else xd / torch.sqrt(s)
+    yd.backward(go.double())
+    def close(mine, ref, rtol):
+        assert float((mine.double() - ref).abs().max()) <= rtol * float(ref.abs().max()) + 1e-7
+    close(x.grad, xd.grad, 2e-5)
+    close(beta_p.grad / (2 * beta_p.detach()), be.grad, 1e-4)
+    close(gamma_p.grad / (2 * gamma_p.detach()), ge.grad, 1e-4)
