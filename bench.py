@@ -72,7 +72,7 @@ def synthetic_batch(batch, H, W, seed, device):
 def cpu_reference(cfg, steps, warmup, batch, dist_name):
     import torch
     from oracle import torch_port as TP
-    from domain_specific_image_compression_b200.losses import multi_scale_ssim   # plain torch, device agnostic
+    multi_scale_ssim = TP.multi_scale_ssim         # the oracle's own restatement of piq: no product code on the CPU arm
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = TP.init_state(cfg["N"], cfg["M"], seed=42, device="cpu")

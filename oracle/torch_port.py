@@ -8,7 +8,7 @@ over a state_dict with the reference's key names, op for op in the reference's o
     GDN            layers.py:19-27          analysis/synthesis/hyper stacks  layers.py:49-73, 81-98, 107-113, 122-152
     quantize       model.py:27-35           forward                          model.py:37-72
     Student-t nll  distributions.py:20-31   Gaussian nll                     distributions.py:39-46
-    loss           model.py:75-107
+    loss           model.py:75-107          MS-SSIM (piq, restated)          model.py:96-101
 
 Pinned against the imported reference by tests/golden/model_small.npz (same weights, same input, same noise).
 Never imported by the product package.
@@ -130,7 +130,49 @@ def forward(sd: Dict[str, torch.Tensor], x, quant_mode="noise", training=True, s
             "z_tilde": z_tilde, "sigma": sigma, "nu": nu}
 
 
+def multi_scale_ssim(x, y, data_range=1.0, scale_weights=None, kernel_size=11, kernel_sigma=1.5, k1=0.01, k2=0.03):
+    """piq.multi_scale_ssim as the reference calls it (model.py:96-101; piq 0.8.0, Requirements.txt).  piq is neither vendored
+    with the reference nor installed here, so this restates its published algorithm (PARITY UNPINNED): 11x11 Gaussian window
+    (sigma 1.5) as a depthwise "valid" convolution, c1 = (k1 L)^2, c2 = (k2 L)^2, 2x2 average pooling between scales
+    (replicate-padding odd sizes on the top/left), relu on the per-scale terms, prod_i cs_i^w_i * ssim_last^w_last with the
+    weights normalised to sum 1, mean over channels then over the batch.  Plain eager PyTorch: this is the oracle's own copy, so
+    that the CPU baseline arm runs none of the product's code."""
+    if scale_weights is None:
+        scale_weights = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], device=x.device, dtype=x.dtype)
+    else:
+        scale_weights = torch.as_tensor(scale_weights, device=x.device, dtype=x.dtype)
+        scale_weights = scale_weights / scale_weights.sum()
+    levels = scale_weights.numel()
+    min_size = (kernel_size - 1) * 2 ** (levels - 1) + 1
+    if x.size(-1) < min_size or x.size(-2) < min_size:
+        raise ValueError(f"Invalid size of the input images, expected at least {min_size}x{min_size}.")
+    x, y = x / float(data_range), y / float(data_range)
+    coords = torch.arange(kernel_size, dtype=x.dtype, device=x.device) - (kernel_size - 1) / 2.0
+    g1 = torch.exp(-(coords ** 2) / (2.0 * kernel_sigma ** 2))
+    g1 = g1 / g1.sum()
+    C = x.size(1)
+    win = (g1[:, None] * g1[None, :])[None, None].repeat(C, 1, 1, 1)
+    c1, c2 = k1 ** 2, k2 ** 2
+    terms = []
+    for level in range(levels):
+        if level > 0:
+            pad = max(x.shape[2] % 2, x.shape[3] % 2)
+            x = F.avg_pool2d(F.pad(x, [pad, 0, pad, 0], mode="replicate"), kernel_size=2, padding=0)
+            y = F.avg_pool2d(F.pad(y, [pad, 0, pad, 0], mode="replicate"), kernel_size=2, padding=0)
+        mu_x, mu_y = F.conv2d(x, win, groups=C), F.conv2d(y, win, groups=C)
+        mu_xx, mu_yy, mu_xy = mu_x * mu_x, mu_y * mu_y, mu_x * mu_y
+        s_xx = F.conv2d(x * x, win, groups=C) - mu_xx
+        s_yy = F.conv2d(y * y, win, groups=C) - mu_yy
+        s_xy = F.conv2d(x * y, win, groups=C) - mu_xy
+        cs_map = (2.0 * s_xy + c2) / (s_xx + s_yy + c2)
+        ss_map = (2.0 * mu_xy + c1) / (mu_xx + mu_yy + c1) * cs_map
+        terms.append((ss_map if level == levels - 1 else cs_map).mean(dim=(-1, -2)))     # [B,C]
+    stacked = torch.relu(torch.stack(terms, dim=0)) ** scale_weights.view(-1, 1, 1)
+    return torch.prod(stacked, dim=0).mean(1).mean(0)
+
+
 def loss_fn(out, x, lambda_rd=10000.0, dist="msssim", msssim=None):
+    msssim = msssim or multi_scale_ssim
     n, _, h, w = x.shape
     R = torch.clamp((out["nll_y"].sum() + out["nll_z"].sum()) / (n * h * w), min=0.0)
     if dist == "mse":

@@ -5,7 +5,6 @@ import torch
 from torch.profiler import profile, ProfilerActivity
 import domain_specific_image_compression_b200 as sic
 from domain_specific_image_compression_b200.trainer import FlatTrainer
-from domain_specific_image_compression_b200.losses import multi_scale_ssim
 from oracle import torch_port as TP
 import bench
 
@@ -53,6 +52,6 @@ if which in ("both", "port"):
     for k, v in sd.items():
         if not k.endswith(".gamma"): v.requires_grad_(True)
     opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-4)
-    stepp = lambda: TP.train_step(sd, opt, x, 10000.0, "msssim", multi_scale_ssim)
+    stepp = lambda: TP.train_step(sd, opt, x, 10000.0, "msssim", TP.multi_scale_ssim)
     print("eager port ms/step", timeit(stepp))
     prof(stepp, "eager port (reference op chains on the GPU)")

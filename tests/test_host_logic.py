@@ -130,6 +130,26 @@ def _msssim_numpy(x, y, weights):
     return np.prod(v ** np.asarray(weights)[:, None, None], axis=0).mean(1).mean(0)
 
 
+def test_oracle_msssim_restatement_matches_independent_evaluation_and_product_statement():
+    """oracle/torch_port.multi_scale_ssim (what the CPU baseline arm runs) against the independent scipy evaluation, and the
+    product's PyTorch statement of the same algorithm (losses.py, the non-fused branch) against the oracle, odd sizes included."""
+    from oracle import torch_port as TP
+    rng = np.random.default_rng(1)
+    w = [0.3, 0.5, 0.2]
+    x = rng.random((2, 3, 64, 64))
+    y = np.clip(x + 0.1 * rng.standard_normal(x.shape), 0, 1)
+    xt, yt = torch.from_numpy(x).float(), torch.from_numpy(y).float()
+    got = float(TP.multi_scale_ssim(xt, yt, 1.0, torch.tensor(w)))
+    assert abs(got - _msssim_numpy(x, y, w)) < 2e-5
+    assert abs(float(TP.multi_scale_ssim(xt, xt, 1.0, torch.tensor(w))) - 1.0) < 1e-6
+    for shape in ((2, 3, 64, 64), (1, 3, 77, 101)):
+        a = torch.rand(*shape, generator=torch.Generator().manual_seed(shape[-1]))
+        b = (a * 0.9 + 0.05).clamp(0, 1)
+        assert abs(float(TP.multi_scale_ssim(a, b, 1.0, torch.tensor(w))) - float(multi_scale_ssim(a, b, 1.0, torch.tensor(w)))) < 1e-6
+    with pytest.raises(ValueError):
+        TP.multi_scale_ssim(torch.rand(1, 3, 32, 32), torch.rand(1, 3, 32, 32), 1.0, torch.tensor(w))
+
+
 def test_msssim_restatement():
     rng = np.random.default_rng(0)
     x = rng.random((2, 3, 64, 64))
