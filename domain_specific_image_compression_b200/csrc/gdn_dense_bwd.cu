@@ -37,6 +37,7 @@ struct OpTraits {
     static constexpr bool kFwd = OP == OP_FWD || OP == OP_FWD_INV;
     static constexpr bool kBwd1 = OP == OP_BWD1 || OP == OP_BWD1_INV;
     static constexpr bool kBwd2 = OP == OP_BWD2;
+    static_assert(OP >= OP_FWD && OP <= OP_BWD2 && (kInverse || !kInverse), "unknown op");
 };
 
 // epilogue tensors:  forward a = x, o0 = y;   pass 1: a = x, b = g, o0 = h, o1 = direct;   pass 2: a = x, b = direct, o0 = dx
