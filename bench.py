@@ -55,6 +55,9 @@ def parse():
                     "internal NCHW<->NHWC transposes; GDN kernels run natively in either layout)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="cuDNN autotune is on by default (warm-up steps absorb it)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--pad-rgb", type=int, default=0, choices=[0, 4, 8], help="zero-pad the image-side channel axis of the first conv / "
+                    "last transposed conv to 4 or 8 so cuDNN can use tensor-core kernels there (layers.PAD_RGB_CHANNELS; identity "
+                    "in exact arithmetic, off by default)")
     return ap.parse_args()
 
 
@@ -190,6 +193,9 @@ def run_ours(args):
     model.train()
     torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     fmt = torch.contiguous_format if args.nchw else torch.channels_last
+    if args.pad_rgb:
+        from domain_specific_image_compression_b200 import layers as _layers
+        _layers.PAD_RGB_CHANNELS = args.pad_rgb
     model = model.to(memory_format=fmt)
     trainer = FlatTrainer(model, lr=1e-4, betas=(0.9, 0.999), grad_clip=1.0)
     x_dev = synthetic_batch(B, H, W, 42 + rank, dev).contiguous(memory_format=fmt)
@@ -281,6 +287,7 @@ def run_ours(args):
                        "l2": "per-step working set (>= 5 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "conv_math": "cuDNN fp32 with TF32 allowed (PyTorch default, as the reference)",
                        "activation_layout": "NCHW" if args.nchw else "channels_last", "launch": graph_note,
+                       "rgb_channel_padding": args.pad_rgb,
                        "cudnn_benchmark": not args.no_cudnn_benchmark},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / K},

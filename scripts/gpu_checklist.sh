@@ -17,6 +17,7 @@ grep -E "k1_bwd|gdn_.*nhwc|dense" $out/${tag}_kernel_bench.log | grep -E "\(16, 
 SIC_DENSE_BWD=1 timeout -k 10 200 python scripts/kernel_bench.py --quick --only dense --json $out/${tag}_kernel_bench_dense_bwd_fused.json 2>&1 | grep -E "dense_bwd|FAILED"
 # 3. the headline line
 timeout 300 python bench.py > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench_1gpu.err; echo "bench rc=$?"; cut -c1-300 $out/${tag}_bench_1gpu.json
+for pad in 4 8; do timeout 300 python bench.py --pad-rgb $pad --no-cpu-baseline > $out/${tag}_bench_1gpu_padrgb$pad.json 2> $out/${tag}_bench_1gpu_padrgb$pad.err; python -c "import json,sys; d=json.load(open('$out/${tag}_bench_1gpu_padrgb$pad.json')); print('pad-rgb $pad:', d['ms_per_step'], 'ms/step', d['value'], 'patches/s')"; done
 # 4. one ncu --set full capture of the changed kernels (never a bench number)
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:"gdn_(fwd|bwd)_nhwc|bottleneck_bwd" -c 4 -f \
     -o $out/${tag}_kernels python scripts/ncu_target.py all 1 > $out/${tag}_ncu_kernels.log 2>&1; echo "ncu rc=$?"

@@ -160,3 +160,30 @@ def test_msssim_restatement():
     assert abs(float(multi_scale_ssim(torch.from_numpy(x).float(), torch.from_numpy(x).float(), 1.0, torch.tensor(w))) - 1.0) < 1e-6
     with pytest.raises(ValueError):
         multi_scale_ssim(torch.rand(1, 3, 32, 32), torch.rand(1, 3, 32, 32), 1.0, torch.tensor(w))   # < 41 px for 3 scales
+
+
+def test_rgb_channel_padding_is_the_identity_and_keeps_parameter_shapes():
+    """layers._rgb_padded (opt-in PAD_RGB_CHANNELS): zero-padding the 3-band axis of the first conv / last transposed conv
+    changes nothing in exact arithmetic and routes the gradients back to the reference-shaped parameters."""
+    import torch.nn as nn
+    from domain_specific_image_compression_b200 import layers as L
+    old = L.PAD_RGB_CHANNELS
+    try:
+        for pad_to in (4, 8):
+            L.PAD_RGB_CHANNELS = pad_to
+            torch.manual_seed(pad_to)
+            c = nn.Conv2d(3, 8, 3, 1, 1)
+            x = torch.rand(2, 3, 16, 16)
+            t, b = L._rgb_padded(c, x)
+            assert b is c.bias and torch.allclose(t + b.view(1, -1, 1, 1), c(x), atol=1e-6)
+            tc, _ = L._rgb_padded(c, x.contiguous(memory_format=torch.channels_last))
+            assert torch.allclose(tc, t, atol=1e-6)
+            d = nn.ConvTranspose2d(8, 3, 5, 2, 2, output_padding=1)
+            z = torch.rand(2, 8, 8, 8)
+            y, b2 = L._rgb_padded(d, z)
+            assert b2 is None and y.shape == (2, 3, 16, 16) and torch.allclose(y, d(z), atol=1e-6)
+            y.sum().backward()
+            assert d.weight.grad.shape == d.weight.shape and d.bias.grad.shape == (3,)
+            assert L._rgb_padded(nn.Conv2d(8, 8, 3), torch.rand(1, 8, 8, 8)) is None       # other layers are left alone
+    finally:
+        L.PAD_RGB_CHANNELS = old
