@@ -13,7 +13,7 @@ SIC_EXPERIMENTAL=1 timeout -k 10 200 python -m pytest tests/test_gpu_gdn.py -m g
 echo "dense bwd rc=$?" | tee -a $out/${tag}_pytest_dense_bwd.log; tail -3 $out/${tag}_pytest_dense_bwd.log
 # 2. kernels against the roofline (K1 sweep top, GDN NCHW/NHWC fwd+bwd, dense fwd both variants + C=192)
 timeout -k 10 300 python scripts/kernel_bench.py --quick --json $out/${tag}_kernel_bench.json > $out/${tag}_kernel_bench.log 2>&1
-grep -E "k1_bwd|gdn_.*nhwc|dense" $out/${tag}_kernel_bench.log | grep -E "\(16, 320, 128, 128\)|\(16, 128, 256, 256\)|\(8, 192" 
+grep -E "k1_bwd|gdn_.*nhwc|dense" $out/${tag}_kernel_bench.log | grep -E "\(16, 320, 128, 128\)|\(16, 128, 256, 256\)|\(16, 128, 128, 128\)|\(8, 192" 
 SIC_DENSE_BWD=1 timeout -k 10 200 python scripts/kernel_bench.py --quick --only dense --json $out/${tag}_kernel_bench_dense_bwd_fused.json 2>&1 | grep -E "dense_bwd|FAILED"
 # 3. the headline line
 timeout 300 python bench.py > $out/${tag}_bench_1gpu.json 2> $out/${tag}_bench_1gpu.err; echo "bench rc=$?"; cut -c1-300 $out/${tag}_bench_1gpu.json
