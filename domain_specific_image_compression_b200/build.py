@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "sic.h"))
     headers.append(os.path.abspath(__file__))
-    objs = []
+    objs, jobs = [], []
     for src, extra in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
@@ -67,9 +67,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if s.endswith(".cpp"):
                 cmd.insert(1, "-x")
                 cmd.insert(2, "cu")
-            if verbose:
-                print(" ".join(cmd), flush=True)
-            subprocess.run(cmd, check=True)
+            jobs.append(cmd)
+
+    def _compile(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+
+    if verbose or len(jobs) <= 1:                      # verbose: keep each file's ptxas report together
+        for cmd in jobs:
+            _compile(cmd)
+    else:                                              # translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            list(pool.map(_compile, jobs))
     if force or _stale(LIB, objs):
         cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
         if verbose:
