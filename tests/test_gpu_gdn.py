@@ -324,3 +324,28 @@ def test_dense_gdn_fused_backward_vs_float64(shape, inverse, monkeypatch):
     close(x.grad, xd.grad, 2e-5)
     close(beta_p.grad / (2 * beta_p.detach()), be.grad, 1e-4)
     close(gamma_p.grad / (2 * gamma_p.detach()), ge.grad, 1e-4)
+
+
+@pytest.mark.parametrize("inverse", [False, True])
+def test_channels_last_backward_full_rounds_and_tail_vs_nchw(inverse):
+    """A site large enough (8.4M elements) that the persistent channels_last backward kernel runs whole rounds of super-chunks
+    AND the finely dealt remainder: its dx must equal the NCHW kernel's (same per-element arithmetic), its parameter and
+    bias gradients the NCHW kernel's up to summation order."""
+    F = _F()
+    g = torch.Generator(device="cuda").manual_seed(17 + inverse)
+    shape = (4, 128, 128, 128)
+    x0 = torch.randn(shape, device="cuda", generator=g) * 2
+    go = torch.randn(shape, device="cuda", generator=g)
+    b0 = torch.sqrt(torch.rand(128, device="cuda", generator=g) + 0.5)
+    w0 = torch.sqrt(torch.rand(128, 1, 1, 1, device="cuda", generator=g) * 0.3 + 0.01)
+    bias0 = torch.randn(128, device="cuda", generator=g) * 0.1
+    res = []
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        x = x0.contiguous(memory_format=fmt).requires_grad_(True)
+        b, w, bias = (t.clone().requires_grad_(True) for t in (b0, w0, bias0))
+        F.gdn(x, b, w, inverse, bias=bias).backward(go.contiguous(memory_format=fmt))
+        res.append((x.grad.contiguous(), b.grad, w.grad, bias.grad))
+    (dx_a, db_a, dw_a, dbias_a), (dx_b, db_b, dw_b, dbias_b) = res
+    assert float((dx_a - dx_b).abs().max()) <= 1e-5 * float(dx_a.abs().max())
+    for a, bb in ((db_a, db_b), (dw_a, dw_b), (dbias_a, dbias_b)):
+        assert float((a - bb).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-6

@@ -196,3 +196,26 @@ def test_model_with_dense_gamma_gdn_on_tensor_cores(N):
     for mod in sites:
         assert mod.gamma.grad is not None and torch.isfinite(mod.gamma.grad).all() and float(mod.gamma.grad.abs().max()) > 0
         assert mod.gamma_conv.weight.grad is None
+
+
+def test_cfg3_full_size_round_trip_and_erasure():
+    """BASELINE.json configs[2] at its own size: N=128, M=192 model on 512x512 patches.  encode -> decode reproduces forward()'s
+    reconstruction bit for bit (both coders emit the same bytes), and dropping the tail of any stream is detected."""
+    import domain_specific_image_compression_b200 as sic
+    torch.manual_seed(3)
+    m = sic.CompressionModel(N=128, M=192, spatial_params=False, min_nu=2.0, max_nu=100.0).cuda().eval()
+    with torch.no_grad():
+        m.g_a.g_a[14].weight.mul_(40.0)             # spread latents (SURVEY 8(d)): default init gives y ~ 0
+        m.h_a.h_a[6].weight.mul_(40.0)
+    x = torch.nn.functional.interpolate(torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(9)), size=(512, 512),
+                                        mode="bilinear").clamp(0, 1).cuda()
+    comp = m.compress(x, tail=10)
+    assert comp["shape_y"] == [2, 192, 32, 32] and comp["shape_z"] == [2, 128, 8, 8]
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True):
+        want = m(x, "round")["x_hat"].clamp(0, 1)
+    assert torch.equal(m.decompress(comp), want)
+    assert m.compress(x, tail=10, coder="host")["strings"] == comp["strings"]
+    bad = dict(comp)
+    bad["strings"] = [[s[0], s[1][: len(s[1]) // 2]] for s in comp["strings"]]
+    with pytest.raises(sic.SicError):
+        m.decompress(bad)
