@@ -133,3 +133,22 @@ def test_sharded_round_trip_on_the_real_model():
         with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True):
             want = m(x[idx], quant_mode="round")["x_hat"].clamp(0, 1)
         assert torch.equal(x_hat, want)
+
+
+# ------------------------------------------------------------------------------------------------ SIC-CONT-1 container
+def test_container_round_trip_and_damage_detection():
+    from domain_specific_image_compression_b200 import container as K
+    codec, x = FakeCodec(), _batch(3)
+    comp = codec.compress(x)
+    blob = K.pack(comp)
+    assert blob[:4] == b"SICC" and len(blob) == 36 + 3 * 24 + sum(len(z) + len(y) for z, y in comp["strings"]) + 4
+    assert K.unpack(blob) == comp
+    assert K.unpack(K.pack(CP.split_compressed(comp, []))) == CP.split_compressed(comp, [])      # zero patches
+    for bad in (blob[:-1], blob[:50], b"XXXX" + blob[4:], blob[:40] + bytes([blob[40] ^ 1]) + blob[41:], blob + b"\0"):
+        with pytest.raises(K.ContainerError):
+            K.unpack(bad)
+    with pytest.raises(K.ContainerError):
+        K.pack({**comp, "min_y": comp["min_y"][:-1]})
+    # negative supports survive (signed fields)
+    neg = {**comp, "min_y": [-37, -1, 0], "min_z": [-2 ** 31, 5, -9]}
+    assert K.unpack(K.pack(neg)) == neg

@@ -213,7 +213,10 @@ def test_cfg3_full_size_round_trip_and_erasure():
     assert comp["shape_y"] == [2, 192, 32, 32] and comp["shape_z"] == [2, 128, 8, 8]
     with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True):
         want = m(x, "round")["x_hat"].clamp(0, 1)
-    assert torch.equal(m.decompress(comp), want)
+    from domain_specific_image_compression_b200 import container
+    blob = container.pack(comp)                                   # SIC-CONT-1: the dict as one self-describing byte string
+    assert container.unpack(blob) == comp
+    assert torch.equal(m.decompress(container.unpack(blob)), want)
     assert m.compress(x, tail=10, coder="host")["strings"] == comp["strings"]
     bad = dict(comp)
     bad["strings"] = [[s[0], s[1][: len(s[1]) // 2]] for s in comp["strings"]]
