@@ -341,7 +341,7 @@ def test_channels_last_backward_full_rounds_and_tail_vs_nchw(inverse):
     bias0 = torch.randn(128, device="cuda", generator=g) * 0.1
     res = []
     for fmt in (torch.contiguous_format, torch.channels_last):
-        x = x0.contiguous(memory_format=fmt).requires_grad_(True)
+        x = x0.detach().clone(memory_format=fmt).requires_grad_(True)
         b, w, bias = (t.clone().requires_grad_(True) for t in (b0, w0, bias0))
         F.gdn(x, b, w, inverse, bias=bias).backward(go.contiguous(memory_format=fmt))
         res.append((x.grad.contiguous(), b.grad, w.grad, bias.grad))
