@@ -326,6 +326,9 @@ def kernel_rooflines(cfg, dev, channels_last=True):
         ts = []
         for _ in range(reps):
             flush.zero_()
+            # a queued spin (~0.2 ms) lets the host run ahead: without it the GPU idles between e0 and the kernel while Python
+            # (autograd dispatch, ~45 us for a backward) is still launching, and that idle time was being billed to the kernel
+            torch.cuda._sleep(400_000)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()

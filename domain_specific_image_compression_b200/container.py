@@ -29,6 +29,26 @@ class ContainerError(ValueError):
     pass
 
 
+MAX_SUPPORT = 4096      # widest support (max - min + 1) the coder's tables hold (csrc/rans_*.c*: kMaxL)
+
+
+def validate_supports(compressed: Dict, B: int) -> None:
+    """Structural checks a CRC cannot give (anyone can recompute a CRC): non-empty latent shapes, min <= max and a support
+    the table builder and the decoder can hold.  decompress() runs this on every dict, whatever its origin."""
+    for k in ("shape_y", "shape_z"):
+        shp = list(compressed[k])
+        if len(shp) != 4 or shp[0] != B or any(int(d) <= 0 for d in shp[1:]) or any(int(d) > (1 << 20) for d in shp[1:]):
+            raise ContainerError(f"{k} = {shp} does not describe {B} non-empty patches")
+    for lo_k, hi_k in (("min_z", "max_z"), ("min_y", "max_y")):
+        lo, hi = list(compressed[lo_k]), list(compressed[hi_k])
+        if len(lo) != B or len(hi) != B:
+            raise ContainerError(f"{lo_k}/{hi_k} have {len(lo)}/{len(hi)} entries for {B} patches")
+        for b in range(B):
+            width = int(hi[b]) - int(lo[b]) + 1
+            if width < 1 or width > MAX_SUPPORT:
+                raise ContainerError(f"patch {b}: support [{int(lo[b])}, {int(hi[b])}] ({lo_k}/{hi_k}) is empty or wider than {MAX_SUPPORT}")
+
+
 def pack(compressed: Dict) -> bytes:
     strings = compressed["strings"]
     B = len(strings)
@@ -67,6 +87,9 @@ def unpack(data: bytes) -> Dict:
         raise ContainerError("container index is truncated")
     entries = [_ENTRY.unpack_from(body, off + b * _ENTRY.size) for b in range(B)]
     off += B * _ENTRY.size
+    validate_supports({"shape_y": [B] + list(dims[:3]), "shape_z": [B] + list(dims[3:]),
+                       "min_y": [e[2] for e in entries], "max_y": [e[3] for e in entries],
+                       "min_z": [e[0] for e in entries], "max_z": [e[1] for e in entries]}, B)
     strings = []
     for (_, _, _, _, lz, ly) in entries:
         if off + lz + ly > len(body):

@@ -38,6 +38,10 @@ __global__ void __launch_bounds__(kWarps * 32) rans_encode_kernel(const int32_t 
     long pos = wcap;  // words are written at [pos, wcap), growing downwards
     uint32_t x = kLow;
     bool bad = false;
+    if (Ls[s] < 1 || Ls[s] > kMaxL || Ls[s] > stride - 1) {   // no support / wider than a table row: nothing can be coded
+        if (lane == 0) out_nbytes[s] = -1;
+        return;
+    }
     const long iters = (n + 31) / 32;
     for (long j = iters - 1; j >= 0; --j) {
         const long i = j * 32 + lane;
@@ -94,7 +98,13 @@ __global__ void __launch_bounds__(kWarps * 32) rans_decode_kernel(const uint8_t 
     const long nw = nb >= 128 ? (nb - 128) / 2 : 0;
     const uint16_t *tab = tables + (long)s * rows_per_stream * stride;
     int32_t *so = sym + (long)s * n;
-    if (nb < 128) {
+    // supports come from a container or a dict the caller did not produce: a patch with min > max gives L <= 0, which as
+    // uint32 would run the staging loop and the binary search far outside the row
+    if (Ls[s] < 1 || Ls[s] > kMaxL || Ls[s] > stride - 1) {
+        if (lane == 0) status[s] = SIC_E_BADARG;
+        return;
+    }
+    if (nb < 128 || nb > cap) {
         if (lane == 0) status[s] = SIC_E_TRUNCATED;
         return;
     }
@@ -149,7 +159,10 @@ __global__ void __launch_bounds__(kWarps * 32) rans_decode_kernel(const uint8_t 
         pos += __popc(mask);
     }
     trunc = __any_sync(0xffffffffu, trunc);
-    if (lane == 0) status[s] = trunc ? SIC_E_TRUNCATED : 0;
+    // a stream that decodes to the end must leave every lane at the encoder's initial state and consume every word:
+    // anything else is damage (flipped bits, stray words) that would otherwise decode silently to garbage
+    const bool corrupt = __any_sync(0xffffffffu, x != kLow) || pos != nw;
+    if (lane == 0) status[s] = trunc ? SIC_E_TRUNCATED : (corrupt ? SIC_E_CORRUPT : 0);
 }
 
 }  // namespace

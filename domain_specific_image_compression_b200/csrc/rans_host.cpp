@@ -120,5 +120,16 @@ extern "C" int sic_rans_decode_host(const uint8_t *in, long nbytes, long n, cons
         }
         sym[i] = lo;
     }
+    // every lane must be back at the encoder's initial state and every word consumed (see rans_device.cu)
+    for (int l = 0; l < kLanes; ++l) {
+        if (state[l] != kLow) {
+            sic::set_error("sic_rans_decode_host: lane %d ends in state 0x%x, not 0x%x: damaged stream", l, state[l], kLow);
+            return SIC_E_CORRUPT;
+        }
+    }
+    if (p != end && p + 1 != end) {   // an odd trailing byte cannot hold a word
+        sic::set_error("sic_rans_decode_host: %ld stray bytes after the last word", (long)(end - p));
+        return SIC_E_CORRUPT;
+    }
     return 0;
 }

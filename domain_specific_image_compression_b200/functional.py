@@ -25,6 +25,13 @@ _workspaces = {}
 _philox = {}
 launch_count = 0          # kernels launched through this module (bench.py reports it as gpu_launches)
 
+# The reference trains under torch.cuda.amp.autocast + GradScaler (train.py:196-204, config.py TRAIN.amp=True): the cuDNN convs
+# then hand float16 activations to GDN and to the likelihood.  The kernels compute in float32 (>= the reference's precision
+# there), so every autograd front end casts its floating inputs up and runs with autocast off; the backward runs in the same
+# state.  Without this the first GDN raised "expected float32" under the reference's default config.
+_amp_fwd = torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_amp_bwd = torch.amp.custom_bwd(device_type="cuda")
+
 
 def _require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
@@ -89,6 +96,7 @@ def _launch(rc: int, what: str) -> None:
 # K1
 class _Bottleneck(torch.autograd.Function):
     @staticmethod
+    @_amp_fwd
     def forward(ctx, y, sigma, nu, mu, noise, quant_mode: int, lik_mode: int, layout: int, want_nll: bool):
         lib = _lib.load()
         y = _require_cuda_f32(y, "y")
@@ -126,6 +134,7 @@ class _Bottleneck(torch.autograd.Function):
         return (y_tilde if quant_mode != QUANT_NONE else None), nll, bits
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, g_yt, g_nll, g_bits):
         lib = _lib.load()
         y_tilde, sigma, nu, mu = ctx.saved_tensors
@@ -176,10 +185,31 @@ def bottleneck(y: torch.Tensor, sigma: torch.Tensor, nu: Optional[torch.Tensor] 
     return (y if y_tilde is None else y_tilde), nll, bits
 
 
+def quantize(x: torch.Tensor, mode: str) -> torch.Tensor:
+    """CompressionModel.quantize (model.py:27-35) on its own: kernel K1 with the likelihood output dropped.  'round' =
+    half-to-even keeping -0.0 (zero gradient, like torch.round); 'noise' = x + U(-1/2, 1/2) from the in-kernel Philox stream
+    (gradient 1).  CUDA float32 only."""
+    if mode not in ("noise", "round"):
+        raise ValueError(f"Unknown quant mode: {mode}")
+    x = _require_cuda_f32(x, "x")
+    if x.numel() == 0:
+        return x
+    flat = x.reshape(1, 1, -1)
+    zero = _zeros1.get(x.device)
+    if zero is None:
+        zero = _zeros1[x.device] = torch.zeros(1, dtype=torch.float32, device=x.device)
+    y_tilde, _, _ = bottleneck(flat, zero, quant=mode, lik="gaussian", want_nll=False)
+    return y_tilde.view(x.shape)
+
+
+_zeros1 = {}
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # K2
 class _GDN(torch.autograd.Function):
     @staticmethod
+    @_amp_fwd
     def forward(ctx, x, beta_param, gamma_weight, inverse: bool, bias=None):
         lib = _lib.load()
         x, cl = _dense_layout(x, "x")
@@ -205,6 +235,7 @@ class _GDN(torch.autograd.Function):
         return y.contiguous(memory_format=torch.channels_last) if back_to_cl else y
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, g):
         lib = _lib.load()
         x, beta_param, gamma_weight, bias = ctx.saved_tensors
@@ -243,6 +274,7 @@ class _GDNDense(torch.autograd.Function):
     (plain library GEMMs, cuBLAS) on the re-parameterised gamma — the dense path is a capability the reference never runs."""
 
     @staticmethod
+    @_amp_fwd
     def forward(ctx, x, beta_param, gamma_param, inverse: bool, variant=None):
         lib = _lib.load()
         if x.dim() != 4:
@@ -266,6 +298,7 @@ class _GDNDense(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, g):
         xc, beta_param, gamma_param = ctx.saved_tensors
         B, C, H, W = xc.shape
@@ -325,6 +358,7 @@ def gdn_dense(x: torch.Tensor, beta_param: torch.Tensor, gamma_param: torch.Tens
 # N3: SSIM statistics of one MS-SSIM scale
 class _SSIMStats(torch.autograd.Function):
     @staticmethod
+    @_amp_fwd
     def forward(ctx, x, y, c1: float, c2: float):
         lib = _lib.load()
         x = _require_cuda_f32(x, "x")
@@ -348,6 +382,7 @@ class _SSIMStats(torch.autograd.Function):
         return means[0].view(B, C), means[1].view(B, C)
 
     @staticmethod
+    @_amp_bwd
     def backward(ctx, g_ss, g_cs):
         lib = _lib.load()
         x, y, maps = ctx.saved_tensors

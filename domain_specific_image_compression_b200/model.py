@@ -16,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as F_sic
+from .container import ContainerError, validate_supports
 from .distributions import FactorizedGaussian, StudentT
 from .layers import AnalysisTransform, HyperAnalysis, HyperSynthesis, SynthesisTransform
 from .losses import multi_scale_ssim
@@ -37,12 +38,12 @@ class CompressionModel(nn.Module):
 
     @staticmethod
     def quantize(x, mode):
-        """model.py:27-35.  Standalone helper kept for API parity; forward() fuses quantisation into kernel K1."""
-        if mode == "noise":
-            return x + torch.empty_like(x).uniform_(-0.5, 0.5)
-        if mode == "round":
-            return torch.round(x)
-        raise ValueError(f"Unknown quant mode: {mode}")
+        """model.py:27-35.  Standalone helper kept for API parity (forward() fuses quantisation into the same kernel together with
+        the likelihood).  Runs kernel K1 in quantise-only form — CUDA float32 only, like every op here; 'noise' draws from the
+        in-kernel Philox stream seeded by torch.manual_seed, not from torch's generator."""
+        if mode not in ("noise", "round"):
+            raise ValueError(f"Unknown quant mode: {mode}")
+        return F_sic.quantize(x, mode)
 
     def _student_params(self, z_tilde, like):
         """model.py:47-55: hyper-synthesis + sigma/nu post-processing.  Returns kernel-layout and dict-layout tensors."""
@@ -144,8 +145,12 @@ class CompressionModel(nn.Module):
             data, lens = self._pack_streams(strings, which, n_sym, dev)
             mins_d, maxs_d = torch.from_numpy(mins).to(dev), torch.from_numpy(maxs).to(dev)
             sym, status = F_sic.rans_decode_device(data, lens, tables, maxs_d - mins_d + 1, n_sym, spr, tables.shape[0] // B)
-            if int(status.abs().max()) != 0:                                  # one sync; erasures must not pass silently
-                raise F_sic._lib.SicError("rANS decoder: truncated stream")
+            st = status.cpu().numpy()                                         # one sync; erasures must not pass silently
+            if st.any():
+                bad = int(np.flatnonzero(st)[0])
+                why = {-5: "truncated stream", -6: "damaged stream (final coder state / word count do not close)",
+                       -1: "support outside what the tables hold"}.get(int(st[bad]), f"status {int(st[bad])}")
+                raise F_sic._lib.SicError(f"rANS decoder: patch {bad}, stream {which}: {why}")
             return (sym + mins_d.view(B, 1)).to(torch.float32)
         tab_h = tables.cpu().numpy().reshape(B, -1, tables.shape[-1])
         lat = np.empty((B, n_sym), np.float32)
@@ -163,6 +168,12 @@ class CompressionModel(nn.Module):
         strings = compressed["strings"]
         shape_y, shape_z = list(compressed["shape_y"]), list(compressed["shape_z"])
         B = len(strings)
+        if B == 0:
+            raise F_sic._lib.SicError("decompress: no patches")
+        try:
+            validate_supports(compressed, B)                                  # min <= max, support <= 4096, non-empty shapes
+        except ContainerError as e:
+            raise F_sic._lib.SicError(f"decompress: {e}") from None
         mnz, mxz = np.asarray(compressed["min_z"], np.int32), np.asarray(compressed["max_z"], np.int32)
         mny, mxy = np.asarray(compressed["min_y"], np.int32), np.asarray(compressed["max_y"], np.int32)
         to_dev = lambda a: torch.from_numpy(a).to(dev)

@@ -8,7 +8,8 @@ into it) so that
   - the all-reduce is a single ncclAllReduce over 25.9 MB (N=128,M=192) / 59.8 MB (N=192,M=320): launch-latency bound on
     NVLink 5, in-switch reduction (NVLS) when NCCL enables it;
   - global-norm clipping and Adam are three launches on the flat buffer instead of ~80 per-tensor launch groups;
-  - the dead `*.gamma` CxC parameters (never used by forward, layers.py:13) are simply left out of the bucket — plain
+  - the dead parameters (per GDN site: the CxC `gamma` on the reference's diagonal path, layers.py:13; `gamma_conv.weight`
+    when the site runs dense) are simply left out of the bucket — plain
     DistributedDataParallel would need find_unused_parameters for them.
 Clipping is applied AFTER the all-reduce so that all ranks scale identically.
 """
@@ -20,8 +21,16 @@ import torch
 import torch.distributed as dist
 
 
-def _is_dead(name: str) -> bool:
-    return name == "gamma" or name.endswith(".gamma")     # GDN's stored-but-unused CxC matrix (layers.py:13)
+def _dead_parameter_names(module: torch.nn.Module) -> set:
+    """Parameters that never receive a gradient, decided per GDN site: the diagonal path (the reference's, layers.py:21) uses
+    `gamma_conv.weight` and leaves the stored CxC `gamma` (layers.py:13) untouched; GDN(dense=True) is the other way round."""
+    from .layers import GDN
+    dead = set()
+    for prefix, m in module.named_modules():
+        if isinstance(m, GDN):
+            dot = prefix + "." if prefix else ""
+            dead.add(dot + ("gamma_conv.weight" if m.dense else "gamma"))
+    return dead
 
 
 def _flat_in_param_order(g: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
@@ -38,12 +47,14 @@ def _is_dense_permutation(p: torch.Tensor) -> bool:
 
 class FlatTrainer:
     def __init__(self, module: torch.nn.Module, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, grad_clip: float = 1.0, process_group=None, fused: Optional[bool] = None):
+                 weight_decay: float = 0.0, grad_clip: float = 1.0, process_group=None, fused: Optional[bool] = None,
+                 exclude: Iterable[str] = ()):
         self.module = module
         self.grad_clip = grad_clip
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
-        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad and not _is_dead(n)]
+        dead = _dead_parameter_names(module) | set(exclude)      # `exclude`: further parameter names the step never touches
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad and n not in dead]
         self.names = [n for n, _ in named]
         self.live: List[torch.nn.Parameter] = [p for _, p in named]
         total = sum(p.numel() for p in self.live)

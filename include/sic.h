@@ -24,7 +24,8 @@ extern "C" {
 
 #define SIC_VERSION 100
 
-enum { SIC_E_BADARG = -1, SIC_E_WORKSPACE = -2, SIC_E_UNSUPPORTED = -3, SIC_E_OVERFLOW = -4, SIC_E_TRUNCATED = -5 };
+enum { SIC_E_BADARG = -1, SIC_E_WORKSPACE = -2, SIC_E_UNSUPPORTED = -3, SIC_E_OVERFLOW = -4, SIC_E_TRUNCATED = -5,
+       SIC_E_CORRUPT = -6 /* a coded stream decodes to the end but not back to the coder's initial state, or leaves words over */ };
 
 /* quantisation of the latent, model.py:27-35 */
 enum {
@@ -168,7 +169,8 @@ int sic_rans_decode_host(const uint8_t *in, long nbytes, long n, const uint16_t 
 /* N1  the same coder on the GPU: one warp per stream, all streams of a batch concurrently; bytes identical to the host coder.
  *   sym [n_streams, n] int32; tables [n_streams * rows_per_stream, stride] uint16; Ls [n_streams] int32 (symbols per
  *   stream's support); out [n_streams, cap] with cap >= 128 + 2n, cap % 4 == 0; out_nbytes [n_streams] (-1: symbol out of
- *   range).  decode: status [n_streams] = 0 or SIC_E_TRUNCATED.  All pointers are DEVICE pointers. */
+ *   range or support L outside [1, min(4096, stride-1)]).  decode: status [n_streams] = 0, SIC_E_TRUNCATED, SIC_E_CORRUPT (final
+ *   states / word count do not close) or SIC_E_BADARG (L outside [1, min(4096, stride-1)]).  All pointers are DEVICE pointers. */
 int sic_rans_encode(const int32_t *sym, const uint16_t *tables, const int32_t *Ls, int n_streams, long n, long sym_per_row,
                     long rows_per_stream, int stride, uint8_t *out, long cap, int32_t *out_nbytes, void *stream);
 int sic_rans_decode(const uint8_t *in, const int32_t *nbytes, const uint16_t *tables, const int32_t *Ls, int n_streams, long n,

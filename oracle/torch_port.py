@@ -130,6 +130,26 @@ def forward(sd: Dict[str, torch.Tensor], x, quant_mode="noise", training=True, s
             "z_tilde": z_tilde, "sigma": sigma, "nu": nu}
 
 
+def ssim_maps(x, y, win, c1, c2):
+    """SSIM map and its contrast-structure factor for one scale: the depthwise "valid" conv2d chain of piq's _ssim_per_channel."""
+    C = x.size(1)
+    mu_x, mu_y = F.conv2d(x, win, groups=C), F.conv2d(y, win, groups=C)
+    mu_xx, mu_yy, mu_xy = mu_x * mu_x, mu_y * mu_y, mu_x * mu_y
+    s_xx = F.conv2d(x * x, win, groups=C) - mu_xx
+    s_yy = F.conv2d(y * y, win, groups=C) - mu_yy
+    s_xy = F.conv2d(x * y, win, groups=C) - mu_xy
+    cs_map = (2.0 * s_xy + c2) / (s_xx + s_yy + c2)
+    ss_map = (2.0 * mu_xy + c1) / (mu_xx + mu_yy + c1) * cs_map
+    return ss_map, cs_map
+
+
+def gaussian_window(channels, size=11, sigma=1.5, dtype=torch.float32, device="cpu"):
+    coords = torch.arange(size, dtype=dtype, device=device) - (size - 1) / 2.0
+    g1 = torch.exp(-(coords ** 2) / (2.0 * sigma ** 2))
+    g1 = g1 / g1.sum()
+    return (g1[:, None] * g1[None, :])[None, None].repeat(channels, 1, 1, 1)
+
+
 def multi_scale_ssim(x, y, data_range=1.0, scale_weights=None, kernel_size=11, kernel_sigma=1.5, k1=0.01, k2=0.03):
     """piq.multi_scale_ssim as the reference calls it (model.py:96-101; piq 0.8.0, Requirements.txt).  piq is neither vendored
     with the reference nor installed here, so this restates its published algorithm (PARITY UNPINNED): 11x11 Gaussian window
@@ -159,13 +179,7 @@ def multi_scale_ssim(x, y, data_range=1.0, scale_weights=None, kernel_size=11, k
             pad = max(x.shape[2] % 2, x.shape[3] % 2)
             x = F.avg_pool2d(F.pad(x, [pad, 0, pad, 0], mode="replicate"), kernel_size=2, padding=0)
             y = F.avg_pool2d(F.pad(y, [pad, 0, pad, 0], mode="replicate"), kernel_size=2, padding=0)
-        mu_x, mu_y = F.conv2d(x, win, groups=C), F.conv2d(y, win, groups=C)
-        mu_xx, mu_yy, mu_xy = mu_x * mu_x, mu_y * mu_y, mu_x * mu_y
-        s_xx = F.conv2d(x * x, win, groups=C) - mu_xx
-        s_yy = F.conv2d(y * y, win, groups=C) - mu_yy
-        s_xy = F.conv2d(x * y, win, groups=C) - mu_xy
-        cs_map = (2.0 * s_xy + c2) / (s_xx + s_yy + c2)
-        ss_map = (2.0 * mu_xy + c1) / (mu_xx + mu_yy + c1) * cs_map
+        ss_map, cs_map = ssim_maps(x, y, win, c1, c2)
         terms.append((ss_map if level == levels - 1 else cs_map).mean(dim=(-1, -2)))     # [B,C]
     stacked = torch.relu(torch.stack(terms, dim=0)) ** scale_weights.view(-1, 1, 1)
     return torch.prod(stacked, dim=0).mean(1).mean(0)

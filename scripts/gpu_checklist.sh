@@ -8,7 +8,7 @@ tag=${1:-r02}
 out=gpurun_out
 mkdir -p $out
 # 1. parity first: the default suite, then the opt-in dense backward (SIC_EXPERIMENTAL=1)
-timeout -k 10 300 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $out/${tag}_pytest_gpu.log
+timeout -k 10 600 python -m pytest tests -m gpu -q > $out/${tag}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $out/${tag}_pytest_gpu.log
 SIC_EXPERIMENTAL=1 timeout -k 10 200 python -m pytest tests/test_gpu_gdn.py -m gpu -q -k fused_backward > $out/${tag}_pytest_dense_bwd.log 2>&1
 echo "dense bwd rc=$?" | tee -a $out/${tag}_pytest_dense_bwd.log; tail -3 $out/${tag}_pytest_dense_bwd.log
 # 2. kernels against the roofline (K1 sweep top, GDN NCHW/NHWC fwd+bwd, dense fwd both variants + C=192)

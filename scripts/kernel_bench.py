@@ -26,6 +26,10 @@ def time_it(fn, reps=args.reps):
     ts = []
     for _ in range(reps):
         flush.zero_()
+        # a queued spin (~0.2 ms) lets the host run ahead of the device: without it the GPU sits idle between e0 and the kernel
+        # while Python is still dispatching (~45 us for an autograd backward) and the idle time is billed to the kernel (r01:
+        # gdn_bwd nhwc 295 us by events vs 252 us under ncu; every backward below 43 us "floor")
+        torch.cuda._sleep(400_000)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))

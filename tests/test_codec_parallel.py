@@ -150,5 +150,9 @@ def test_container_round_trip_and_damage_detection():
     with pytest.raises(K.ContainerError):
         K.pack({**comp, "min_y": comp["min_y"][:-1]})
     # negative supports survive (signed fields)
-    neg = {**comp, "min_y": [-37, -1, 0], "min_z": [-2 ** 31, 5, -9]}
+    neg = {**comp, "min_y": [-37, -1, 0], "min_z": [-3000, 5, -9]}
     assert K.unpack(K.pack(neg)) == neg
+    # ... but a support no table can hold (wider than 4096 symbols, or max < min) is refused although the CRC is right
+    for k, v in (("min_z", [-2 ** 31, 5, -9]), ("max_y", [-40, 264, 264])):
+        with pytest.raises(K.ContainerError):
+            K.unpack(K.pack({**comp, k: v}))

@@ -334,3 +334,20 @@ def test_empty_inputs():
     assert nll.numel() == 0 and bits.tolist() == [0.0, 0.0]
     x = torch.zeros(0, 16, 8, 8, device="cuda")
     assert F.gdn(x, torch.ones(16, device="cuda"), torch.ones(16, 1, 1, 1, device="cuda")).shape == x.shape
+
+
+def test_static_quantize_helper_runs_the_kernel():
+    """CompressionModel.quantize (model.py:27-35) as a standalone call: half-to-even with the sign of zero kept, zero gradient
+    for 'round' (torch.round), unit gradient and |noise| <= 1/2 for 'noise'."""
+    import domain_specific_image_compression_b200 as sic
+    x = torch.tensor([0.5, 1.5, 2.5, -0.5, -0.4, 3.49], device="cuda")
+    q = sic.CompressionModel.quantize(x, "round")
+    assert torch.equal(q.view(torch.int32), torch.tensor([0.0, 2.0, 2.0, -0.0, -0.0, 3.0], device="cuda").view(torch.int32))
+    big = torch.randn(3, 5, 7, 11, device="cuda", requires_grad=True)
+    n = sic.CompressionModel.quantize(big, "noise")
+    assert n.shape == big.shape and float((n - big).abs().max()) <= 0.5 and float((n - big).abs().max()) > 0.3
+    n.sum().backward()
+    assert torch.equal(big.grad, torch.ones_like(big))
+    big.grad = None
+    sic.CompressionModel.quantize(big, "round").sum().backward()
+    assert float(big.grad.abs().max()) == 0.0

@@ -222,3 +222,25 @@ def test_cfg3_full_size_round_trip_and_erasure():
     bad["strings"] = [[s[0], s[1][: len(s[1]) // 2]] for s in comp["strings"]]
     with pytest.raises(sic.SicError):
         m.decompress(bad)
+
+
+def test_training_step_under_autocast_like_the_reference(golden):
+    """train.py:196-204 runs forward + loss under torch.cuda.amp.autocast with a GradScaler (config.py TRAIN.amp=True).  The cuDNN
+    convs then return float16; our kernels take it (cast up, computed in float32) instead of raising, and every live
+    parameter receives a finite float32 gradient.  Loss within float16 conv error of the float32 run."""
+    import domain_specific_image_compression_b200 as sic
+    m, G = _model(golden)
+    m.train()
+    x = torch.from_numpy(G["x"]).cuda()
+    ny, nz = torch.from_numpy(G["train.noise_y"]).cuda(), torch.from_numpy(G["train.noise_z"]).cuda()
+    out32 = m(x, quant_mode="noise", noise_y=ny, noise_z=nz)
+    loss32, _, _ = sic.rate_distortion_loss(out32, x, lambda_rd=100.0, dist="msssim")
+    scaler = torch.amp.GradScaler("cuda")
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = m(x, quant_mode="noise", noise_y=ny, noise_z=nz)
+        loss, Rr, D = sic.rate_distortion_loss(out, x, lambda_rd=100.0, dist="msssim")
+    assert out["y_tilde"].dtype == torch.float32 and out["nll_y"].dtype == torch.float32     # kernel outputs stay float32
+    assert abs(float(loss) - float(loss32)) < 0.05 * abs(float(loss32)) + 1e-2
+    scaler.scale(loss).backward()
+    live = [(n, p) for n, p in m.named_parameters() if not n.endswith(".gamma")]
+    assert all(p.grad is not None and p.grad.dtype == torch.float32 and torch.isfinite(p.grad).all() for _, p in live)

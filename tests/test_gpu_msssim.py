@@ -1,8 +1,10 @@
 """N3: fused SSIM-statistics kernels (one forward + one backward launch per MS-SSIM scale) against the PyTorch statement
-of the same algorithm (losses._ssim_and_cs: depthwise conv2d chain) and a float64 numpy evaluation."""
+of the same algorithm in the oracle (oracle/torch_port.ssim_maps / multi_scale_ssim: depthwise conv2d chain, float64)."""
 import numpy as np
 import pytest
 import torch
+
+from oracle import torch_port as TP
 
 pytestmark = pytest.mark.gpu
 
@@ -24,8 +26,8 @@ def test_ssim_stats_forward_backward_vs_conv_chain(shape):
     ss, cs = F.ssim_stats(xa, y)
     ((ss * gs).sum() + (cs * gc).sum()).backward()
     xb = x0.double().clone().requires_grad_(True)
-    win = losses._gaussian_window(11, 1.5, x0.device, torch.float64).repeat(shape[1], 1, 1, 1)
-    ss_r, cs_r = losses._ssim_and_cs(xb, y.double(), win, 0.01 ** 2, 0.03 ** 2)
+    win = TP.gaussian_window(shape[1], 11, 1.5, torch.float64, x0.device)
+    ss_r, cs_r = (m.mean(dim=(-1, -2)) for m in TP.ssim_maps(xb, y.double(), win, 0.01 ** 2, 0.03 ** 2))
     ((ss_r * gs.double()).sum() + (cs_r * gc.double()).sum()).backward()
     assert float((ss.double() - ss_r).abs().max()) < 2e-6 and float((cs.double() - cs_r).abs().max()) < 2e-6
     assert float((xa.grad.double() - xb.grad).abs().max()) <= 2e-5 * float(xb.grad.abs().max()) + 1e-9
@@ -33,7 +35,7 @@ def test_ssim_stats_forward_backward_vs_conv_chain(shape):
         F.ssim_stats(torch.rand(1, 3, 10, 30, device="cuda"), torch.rand(1, 3, 10, 30, device="cuda"))
 
 
-def test_multi_scale_ssim_fused_equals_unfused(monkeypatch):
+def test_multi_scale_ssim_kernel_vs_oracle_chain():
     F, losses = _mods()
     g = torch.Generator(device="cuda").manual_seed(0)
     y = torch.rand(4, 3, 256, 256, device="cuda", generator=g)
@@ -44,9 +46,8 @@ def test_multi_scale_ssim_fused_equals_unfused(monkeypatch):
     va = losses.multi_scale_ssim(xa.clamp(0, 1), y, 1.0, w)
     va.backward()
     assert F.launch_count - n0 == 6                         # 3 scales x (1 forward + 1 backward kernel)
-    monkeypatch.setattr(losses, "_fused_ok", lambda *a, **k: False)
     xb = x0.clone().requires_grad_(True)
-    vb = losses.multi_scale_ssim(xb.clamp(0, 1), y, 1.0, w)
+    vb = TP.multi_scale_ssim(xb.clamp(0, 1), y, 1.0, w)      # the oracle's conv2d chain on the same device
     vb.backward()
     assert abs(float(va) - float(vb)) < 2e-6
     assert float((xa.grad - xb.grad).abs().max()) <= 1e-4 * float(xb.grad.abs().max()) + 1e-10
@@ -54,6 +55,17 @@ def test_multi_scale_ssim_fused_equals_unfused(monkeypatch):
     assert abs(float(losses.multi_scale_ssim(y, y, 1.0, w)) - 1.0) < 1e-6
     z = torch.rand(2, 3, 101, 77, device="cuda", generator=g)
     a = losses.multi_scale_ssim(z.contiguous(memory_format=torch.channels_last), z * 0.9, 1.0, w)
-    monkeypatch.undo()
-    b = losses.multi_scale_ssim(z, z * 0.9, 1.0, w)
+    b = TP.multi_scale_ssim(z, z * 0.9, 1.0, w)
     assert abs(float(a) - float(b)) < 2e-6
+    # float16 reconstructions (the reference's autocast training) are computed in float32 by the kernel
+    c = losses.multi_scale_ssim(z.half(), z * 0.9, 1.0, w)
+    assert abs(float(c) - float(b)) < 2e-3
+
+
+def test_no_cpu_path_for_the_loss():
+    """north_star: no CPU fallback.  The distortion term raises on CPU tensors like every other op of the package."""
+    import domain_specific_image_compression_b200 as sic
+    _, losses = _mods()
+    w = torch.tensor([0.3, 0.5, 0.2])
+    with pytest.raises(sic.SicError):
+        losses.multi_scale_ssim(torch.rand(1, 3, 64, 64), torch.rand(1, 3, 64, 64), 1.0, w)

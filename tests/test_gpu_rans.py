@@ -77,6 +77,40 @@ def test_device_coder_spatial_rows_and_errors():
     assert int(nb[0]) == -1
 
 
+def test_device_decoder_reports_damage_and_bad_supports():
+    """Flipped bits / stray words must come back as SIC_E_CORRUPT (-6) or SIC_E_TRUNCATED (-5), never as symbols; a support
+    L <= 0 (min > max in a hand-made container) or L wider than the table row is SIC_E_BADARG (-1) and touches no memory."""
+    F = _F()
+    rng = np.random.default_rng(5)
+    S, C, hw, L = 4, 6, 64, 9
+    n = C * hw
+    pm = rng.random((S, C, L)) + 0.05
+    cdf = np.concatenate([np.zeros((S, C, 1)), np.cumsum(pm / pm.sum(-1, keepdims=True), -1)], -1)
+    cdf[..., -1] = 1.0
+    tabs = np.zeros((S, C, L + 3), np.uint16)
+    tabs[..., :L + 1] = (cdf * 65535).astype(np.uint16)
+    syms = rng.integers(0, L, (S, n)).astype(np.int32)
+    t_d = torch.from_numpy(tabs.reshape(S * C, -1)).cuda()
+    Ls = torch.full((S,), L, dtype=torch.int32).cuda()
+    out, nb = F.rans_encode_device(torch.from_numpy(syms).cuda(), t_d, Ls, hw, C)
+    dec, st = F.rans_decode_device(out, nb, t_d, Ls, n, hw, C)
+    assert st.abs().max().item() == 0 and np.array_equal(dec.cpu().numpy(), syms)
+    hurt = out.clone()
+    hurt[0, 5] ^= 0x40                                   # a state word
+    hurt[1, 140] ^= 0x01                                 # an early renormalisation word
+    hurt[2, int(nb[2]) - 1] ^= 0x80                      # the last word
+    nb2 = nb.clone(); nb2[3] += 2                        # one stray (zero) word after stream 3
+    _, st = F.rans_decode_device(hurt, nb2, t_d, Ls, n, hw, C)
+    st = st.cpu().numpy()
+    assert all(int(v) in (-5, -6) for v in st), st
+    badL = torch.tensor([0, -3, L + 3, 5000], dtype=torch.int32).cuda()
+    _, st = F.rans_decode_device(out, nb, t_d, badL, n, hw, C)
+    assert st.cpu().tolist() == [-1, -1, -1, -1]
+    _, nbe = F.rans_encode_device(torch.from_numpy(syms).cuda(), t_d, badL, hw, C)
+    assert nbe.cpu().tolist() == [-1, -1, -1, -1]
+    torch.cuda.synchronize()
+
+
 def test_compress_gpu_and_host_coders_agree(golden):
     import domain_specific_image_compression_b200 as sic
     G = golden("model_small")

@@ -31,7 +31,7 @@ def test_flat_trainer_equals_reference_step():
     torch.manual_seed(0)
     m = Toy()
     ref = copy.deepcopy(m)
-    tr = FlatTrainer(m, lr=1e-2, grad_clip=1.0, fused=False)
+    tr = FlatTrainer(m, lr=1e-2, grad_clip=1.0, fused=False, exclude=["gamma"])
     assert "gamma" not in tr.names and tr.flat.numel() == sum(p.numel() for n, p in ref.named_parameters() if n != "gamma")
     opt = torch.optim.Adam([p for n, p in ref.named_parameters() if n != "gamma"], lr=1e-2)
     x = torch.rand(4, 3, 8, 8)
@@ -47,9 +47,20 @@ def test_flat_trainer_equals_reference_step():
     assert m.a.weight.data_ptr() == tr.flat.data_ptr()
 
 
+def test_dead_parameters_follow_the_gdn_mode():
+    """Per GDN site: the reference's diagonal path trains `gamma_conv.weight` and never touches the CxC `gamma` (layers.py:13,21);
+    GDN(dense=True) trains `gamma` and never touches `gamma_conv.weight`.  The bucket must hold exactly the live ones."""
+    from domain_specific_image_compression_b200.layers import GDN
+    from domain_specific_image_compression_b200.trainer import _dead_parameter_names
+    m = torch.nn.Sequential(GDN(4), torch.nn.Sequential(GDN(4, inverse=True, dense=True)))
+    assert _dead_parameter_names(m) == {"0.gamma", "1.0.gamma_conv.weight"}
+    tr = FlatTrainer(m, fused=False)
+    assert tr.names == ["0.beta", "0.gamma_conv.weight", "1.0.beta", "1.0.gamma"]
+
+
 def test_missing_gradient_is_reported():
     m = Toy()
-    tr = FlatTrainer(m, fused=False)
+    tr = FlatTrainer(m, fused=False, exclude=["gamma"])
     with pytest.raises(RuntimeError):
         tr.step(lambda: m.a(torch.rand(1, 3, 4, 4)).sum())      # m.b gets no gradient
 
@@ -67,7 +78,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(100 + rank)                  # different initial weights per rank: the broadcast must fix that
     m = Toy()
-    tr = FlatTrainer(m, lr=1e-2, grad_clip=0.5, fused=False)
+    tr = FlatTrainer(m, lr=1e-2, grad_clip=0.5, fused=False, exclude=["gamma"])
     g = torch.Generator().manual_seed(7)
     x_all = torch.rand(4, 3, 8, 8, generator=g)
     x = x_all[rank * 2:(rank + 1) * 2]             # patches shard across ranks
@@ -93,7 +104,7 @@ def test_two_ranks_gloo_equal_single_process_on_full_batch():
     assert torch.equal(got[0], got[1])             # replicas stay identical
     torch.manual_seed(100)                         # rank 0's initial weights
     m = Toy()
-    tr = FlatTrainer(m, lr=1e-2, grad_clip=0.5, fused=False)
+    tr = FlatTrainer(m, lr=1e-2, grad_clip=0.5, fused=False, exclude=["gamma"])
     x_all = torch.rand(4, 3, 8, 8, generator=torch.Generator().manual_seed(7))
     for _ in range(3):
         tr.step(lambda: _loss(m, x_all))           # mean over 4 patches == mean of the two ranks' means over 2 patches
