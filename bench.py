@@ -9,12 +9,15 @@ One "step" = the reference's training step (train.py:193-204 without AMP: forwar
 one flat-bucket NCCL all-reduce per step for N > 1.  Prints ONE JSON line (rank 0).
   value     patches/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e       same metric through the public API with the batch coming from pinned HOST memory every step and the loss read
-            back to the host every step
+            back to the host every step (trainer.HostFedLoop: copies on a copy stream, loss handed back one step late)
   roofline  dominant own kernel of the step (GDN backward in the step's layout): algorithmic bytes / CUDA-event time,
-            measured in this run
-  cpu_baseline  the reference's eager op chains (oracle/torch_port.py — /root/reference itself cannot travel to the GPU box)
-            on the host cores, bounded sample
---impl reference: only the CPU arm (rank 0), same metric/config/unit.
+            measured in this run; `traffic` from the committed ncu capture of the SAME register allocation
+            (profiles/ncu_traffic.json vs sic_kernel_registers of the loaded library), else null
+  cpu_baseline  the reference's eager op chains (oracle/torch_port.py, kind "port": /root/reference itself cannot travel to
+            the GPU box; the port is pinned bit-for-bit against the imported reference by tests/test_oracle_golden.py) on
+            the host cores, bounded sample, median step
+  gpu_eager_baseline  the same eager op chains on THIS GPU (fp32, NCHW, same cuDNN flags): the bar the fused kernels must beat
+--impl reference: only the CPU arm (rank 0), same metric/config/unit, the caller's --steps/--warmup honoured.
 """
 from __future__ import annotations
 
@@ -49,8 +52,13 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--dist", default="msssim", choices=["msssim", "mse"])
-    ap.add_argument("--ref-batch", type=int, default=2, help="patches per CPU step of the reference arm (bounded sample)")
+    ap.add_argument("--ref-batch", type=int, default=0, help="patches per CPU step of the CPU arms (bounded sample); 0 = 8 for "
+                    "N<=128 (BASELINE.json configs[0] runs the CPU case at batch 8), 4 for the larger model")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-eager-baseline", action="store_true")
+    ap.add_argument("--gdn", default="diag", choices=["diag", "dense"], help="diag: the reference's path (layers.py:21); dense: all 13 "
+                    "GDN/IGDN sites use the C x C gamma on tcgen05 tensor cores (north_star's contraction), forward and backward")
+    ap.add_argument("--bucket-mb", type=float, default=6.0, help="gradient bucket size for the overlapped all-reduce")
     ap.add_argument("--nchw", action="store_true", help="keep activations NCHW (default: torch.channels_last, which saves cuDNN's "
                     "internal NCHW<->NHWC transposes; GDN kernels run natively in either layout)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="cuDNN autotune is on by default (warm-up steps absorb it)")
@@ -72,7 +80,13 @@ def synthetic_batch(batch, H, W, seed, device):
 
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's eager op chains on the host cores
+def ref_batch(args, cfg):
+    return args.ref_batch if args.ref_batch > 0 else (8 if cfg["N"] <= 128 else 4)
+
+
 def cpu_reference(cfg, steps, warmup, batch, dist_name):
+    """-> (patches/s from the MEDIAN step, median ms/step, cores, all step times).  Median, not mean: the first steps after the
+    warm-up still pay allocator / oneDNN primitive-cache effects, which made two runs of the same code differ by 1.5x in round 1."""
     import torch
     from oracle import torch_port as TP
     multi_scale_ssim = TP.multi_scale_ssim         # the oracle's own restatement of piq: no product code on the CPU arm
@@ -86,11 +100,13 @@ def cpu_reference(cfg, steps, warmup, batch, dist_name):
     x = synthetic_batch(batch, cfg["H"], cfg["W"], 42, "cpu")
     for _ in range(warmup):
         TP.train_step(sd, opt, x, LAMBDA_RD, dist_name, multi_scale_ssim)
-    t0 = time.perf_counter()
+    times = []
     for _ in range(steps):
+        t0 = time.perf_counter()
         TP.train_step(sd, opt, x, LAMBDA_RD, dist_name, multi_scale_ssim)
-    dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps * 1e3, cores
+        times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    return batch / med, med * 1e3, cores, [t * 1e3 for t in times]
 
 
 def run_reference_arm(args):
@@ -98,19 +114,51 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cfg = CONFIGS[args.config]
-    steps, warmup = max(1, args.steps), max(0, args.warmup)
-    # keep the whole run within a few minutes whatever K/W the caller passes: ~6 s of CPU work per step at 8 cores
-    value, ms, cores = cpu_reference(cfg, steps, min(warmup, 2), args.ref_batch, args.dist)
-    sample = f"{args.ref_batch} patches/step x {steps} steps (+{min(warmup, 2)} warm-up) of the {args.config} training step"
+    steps, warmup, rb = max(1, args.steps), max(0, args.warmup), ref_batch(args, cfg)
+    # bounded sample: rb patches per step (~1.2 s of CPU work per step on 16 cores), so the default 20 + 5 steps end in ~30 s
+    value, ms, cores, times = cpu_reference(cfg, steps, warmup, rb, args.dist)
+    sample = (f"{rb} patches/step x {steps} timed steps (after {warmup} warm-up steps) of the {args.config} training step; value = "
+              f"patches / median step; oracle/torch_port.py eager fp32 (bit-equal to the imported reference on CPU)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args, cfg), "batch_per_step": args.ref_batch, "parallelism": "cpu"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args, cfg), "batch_per_step": rb, "parallelism": "cpu"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "step_ms_min_median_max": [min(times), ms, max(times)]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
+
+
+def gpu_eager_reference(cfg, dev, dist_name, batch, steps=3, warmup=2):
+    """The reference's eager op chains (oracle/torch_port.py) on THIS GPU: fp32, NCHW (the reference's layout), TF32 convs allowed
+    and cuDNN autotune on exactly like our arm, no AMP (BASELINE configs are fp32).  CUDA-event timed, median step."""
+    import torch
+    from oracle import torch_port as TP
+    sd = TP.init_state(cfg["N"], cfg["M"], seed=42, device=dev)
+    for k, v in sd.items():
+        if not k.endswith(".gamma"):
+            v.requires_grad_(True)
+    opt = torch.optim.Adam([v for v in sd.values() if v.requires_grad], lr=1e-4)
+    x = synthetic_batch(batch, cfg["H"], cfg["W"], 42, dev)
+    for _ in range(warmup):
+        TP.train_step(sd, opt, x, LAMBDA_RD, dist_name, TP.multi_scale_ssim)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        TP.train_step(sd, opt, x, LAMBDA_RD, dist_name, TP.multi_scale_ssim)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    med = sorted(times)[len(times) // 2]
+    del sd, opt, x
+    torch.cuda.empty_cache()
+    return {"value": batch / (med * 1e-3), "unit": UNIT, "ms_per_step": med, "batch": batch, "steps": steps, "warmup": warmup,
+            "what": "oracle/torch_port.py (the reference's op chains, eager PyTorch) on this GPU: fp32, NCHW, cudnn.benchmark on, TF32 convs allowed, "
+                    "no CUDA graph, restated MS-SSIM; inputs resident"}
 
 
 def workload_name(args, cfg):
@@ -164,7 +212,7 @@ def run_ours(args):
     import torch.distributed as dist
     import domain_specific_image_compression_b200 as sic
     from domain_specific_image_compression_b200 import functional as F_sic
-    from domain_specific_image_compression_b200.trainer import FlatTrainer
+    from domain_specific_image_compression_b200.trainer import FlatTrainer, HostFedLoop
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl ours) needs a CUDA device: the product has no CPU path")
@@ -182,6 +230,14 @@ def run_ours(args):
     B, H, W = cfg["batch"], cfg["H"], cfg["W"]
     # kernel rooflines first: they draw from torch's CUDA generator, which must not be touched between graph replays
     roof, kernels = kernel_rooflines(cfg, dev, channels_last=not args.nchw) if rank == 0 else (None, None)
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager_baseline:
+        try:
+            gpu_eager = gpu_eager_reference(cfg, dev, args.dist, min(B, 16))
+        except Exception as e:                                   # a comparator must never take the measurement down with it
+            gpu_eager = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+            torch.cuda.empty_cache()
     if world > 1:
         dist.barrier()
     torch.manual_seed(42)                                      # config.py:32
@@ -190,18 +246,21 @@ def run_ours(args):
         model.g_a.g_a[14].weight.mul_(40.0)
         model.h_a.h_a[6].weight.mul_(40.0)
         model.h_s.mlp_nu[2].bias.add_(1.5)
+    if args.gdn == "dense":                                    # north_star's G3 at every site; gamma (C x C) becomes the live parameter
+        from domain_specific_image_compression_b200.layers import GDN as _GDN
+        for mod in model.modules():
+            if isinstance(mod, _GDN):
+                mod.dense = True
     model.train()
-    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     fmt = torch.contiguous_format if args.nchw else torch.channels_last
     if args.pad_rgb:
         from domain_specific_image_compression_b200 import layers as _layers
         _layers.PAD_RGB_CHANNELS = args.pad_rgb
     model = model.to(memory_format=fmt)
-    trainer = FlatTrainer(model, lr=1e-4, betas=(0.9, 0.999), grad_clip=1.0)
+    trainer = FlatTrainer(model, lr=1e-4, betas=(0.9, 0.999), grad_clip=1.0, bucket_bytes=int(args.bucket_mb * (1 << 20)))
     x_dev = synthetic_batch(B, H, W, 42 + rank, dev).contiguous(memory_format=fmt)
     x_host = x_dev.cpu().pin_memory()
     x_stage = torch.empty_like(x_dev)
-    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def closure_on(xin):
         def closure():
@@ -220,7 +279,7 @@ def run_ours(args):
             lc0 = F_sic.launch_count
             run_static = trainer.capture(closure_on(x_stage), warmup=n_cap)
             launches_per_step = (F_sic.launch_count - lc0) // (n_cap + 1)     # our kernels recorded per replayed step
-            graph_note = "whole step (zero_grad..Adam, incl. the all-reduce) replayed as one CUDA graph"
+            graph_note = "whole step (zero_grad..Adam, incl. the bucketed all-reduces overlapped with backward) replayed as one CUDA graph"
         except Exception as e:                                   # fall back loudly, never silently
             print(f"[bench] CUDA graph capture failed, running eagerly: {type(e).__name__}: {e}", file=sys.stderr)
             run_static = None
@@ -229,11 +288,17 @@ def run_ours(args):
     def step_resident():                                         # inputs already resident in HBM (x_stage holds the batch)
         return run_static() if run_static is not None else trainer.step(closure_on(x_stage))
 
+    # end to end: every step's batch comes from pinned host memory and every step's loss goes back to the host; the copies run on
+    # a copy stream next to the previous / next step's kernels and the loss is read one step late (trainer.HostFedLoop)
+    feed = HostFedLoop(step_resident, x_stage)
+    e2e_losses = []
+
     def step_e2e():
-        x_stage.copy_(x_host, non_blocking=True)                 # H2D of this step's patches (pinned)
-        loss = run_static() if run_static is not None else trainer.step(closure_on(x_stage))
-        loss_host.copy_(loss, non_blocking=False)                # D2H of the step's result
-        return loss_host
+        if not feed._staged:
+            feed.stage(x_host)
+        prev = feed.step(x_host)                                 # runs this step, starts the next batch's H2D, returns the previous loss
+        if prev is not None:
+            e2e_losses.append(prev)
 
     def barrier():
         if world > 1:
@@ -267,7 +332,24 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
-    ms_e2e = timed(step_e2e, K)
+
+    def timed_e2e(steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_e2e()
+        e2e_losses.append(feed.drain())                          # the last step's loss is on the host before the clock stops
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    ms_e2e = timed_e2e(K)
+    if not all(l == l and abs(l) < 1e30 for l in e2e_losses):
+        raise SystemExit(f"[bench] non-finite loss in the end-to-end loop: {e2e_losses[-3:]}")
     value = B * world * K / (ms_total / 1e3)
     e2e_value = B * world * K / (ms_e2e / 1e3)
 
@@ -275,10 +357,13 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # bounded sample (~10 s of CPU work on the box's cores): 3 timed steps of 8 patches (BASELINE.json configs[0] runs the
         # CPU case at batch 8) after 1 warm-up step; cfg4's model is 2.3x the work per patch, so it gets 4 patches
-        cb = 8 if cfg["N"] <= 128 else 4
-        v, ms, cores = cpu_reference(cfg, 3, 1, cb, args.dist)
+        cb = ref_batch(args, cfg)
+        v, ms, cores, times = cpu_reference(cfg, 5, 2, cb, args.dist)
         cpu_base = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"3 steps of {cb} patches (after 1 warm-up step) of the {args.config} training step, oracle/torch_port.py eager fp32"}
+                    "sample": f"{cb} patches/step x 5 timed steps (after 2 warm-up steps) of the {args.config} training step; value = patches / "
+                              f"median step; oracle/torch_port.py eager fp32 (bit-equal to the imported reference on CPU) — the same "
+                              f"function, batch and statistic as `bench.py --impl reference`",
+                    "step_ms_min_median_max": [min(times), ms, max(times)]}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms_total / K,
@@ -287,22 +372,25 @@ def run_ours(args):
                        "l2": "per-step working set (>= 5 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "conv_math": "cuDNN fp32 with TF32 allowed (PyTorch default, as the reference)",
                        "activation_layout": "NCHW" if args.nchw else "channels_last", "launch": graph_note,
-                       "rgb_channel_padding": args.pad_rgb,
+                       "rgb_channel_padding": args.pad_rgb, "gdn": args.gdn,
+                       "gradient_buckets": [hi - lo for lo, hi, _, _ in trainer.buckets] if world > 1 else None,
                        "cudnn_benchmark": not args.no_cudnn_benchmark},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
-                    "ms_per_step": ms_e2e / K},
+                    "ms_per_step": ms_e2e / K, "last_loss": e2e_losses[-1],
+                    "how": "HostFedLoop: pinned batch -> copy stream -> landing buffer -> static input; loss -> pinned host, read one step late"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base,
+            "gpu_eager_baseline": gpu_eager,
             "allreduce_bytes_per_step": trainer.nbytes_allreduce if world > 1 else 0,
         }
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
-        # Tearing a process group down while a captured CUDA graph still references its NCCL kernels can hang
-        # (observed at 8 ranks: the JSON line was out, then destroy_process_group() never returned).  Everything has been
-        # measured and printed: synchronise, meet the other ranks once more, and leave without running the teardown.
+        # Round 1 left through os._exit: destroy_process_group() hung at 8 ranks while the captured graph (which holds the NCCL
+        # kernels) was still alive.  Order matters: drop the graph first, then meet, then tear the communicator down.
+        trainer.release_graph()
+        del feed, run_static
         torch.cuda.synchronize()
         dist.barrier()
-        sys.stdout.flush(); sys.stderr.flush()
-        os._exit(0)
+        dist.destroy_process_group()
 
 
 def kernel_rooflines(cfg, dev, channels_last=True):
@@ -367,34 +455,87 @@ def kernel_rooflines(cfg, dev, channels_last=True):
         t = time_it(lambda: F.bottleneck(yl, sg, nu, quant="noise"))
         ne = yl.numel()
         out[tag] = {"shape": list(shape), "bytes": 12 * ne, "ms": t * 1e3, "gbs": 12 * ne / t / 1e9}
+        if tag == "k1_fwd_sweep_top":
+            # backward (8 B/elem + 4 for the dense upstream of y_tilde), spatial sigma/nu forward (20 B/elem) and the cdf_diff
+            # likelihood (north_star's named kernel: SFU/issue-bound, so it is quoted in elements/s and MUFU thread-ops/s)
+            yr, sr, nr = yl.clone().requires_grad_(True), sg.clone().requires_grad_(True), nu.clone().requires_grad_(True)
+            yt, _, bits = F.bottleneck(yr, sr, nr, quant="noise")
+            gb, gy = torch.ones_like(bits), torch.randn_like(yt)
+            t = time_it(lambda: torch.autograd.grad((bits, yt), (yr, sr, nr), (gb, gy), retain_graph=True))
+            out["k1_bwd_sweep_top"] = {"shape": list(shape), "bytes": 12 * ne, "ms": t * 1e3, "gbs": 12 * ne / t / 1e9}
+            del yr, yt, gy
+            ss, ns = sg.expand_as(yl).contiguous(), nu.expand_as(yl).contiguous()
+            t = time_it(lambda: F.bottleneck(yl, ss, ns, quant="noise"))
+            out["k1_fwd_spatial_sweep_top"] = {"shape": list(shape), "bytes": 20 * ne, "ms": t * 1e3, "gbs": 20 * ne / t / 1e9}
+            del ss, ns
+            t = time_it(lambda: F.bottleneck(yl, sg, nu, quant="noise", lik="cdf_diff"), reps=5)
+            row = {"shape": list(shape), "bytes": 12 * ne, "ms": t * 1e3, "gbs": 12 * ne / t / 1e9, "bound": "sfu/issue (not hbm)",
+                   "gelem_per_s": ne / t / 1e9}
+            pipes = _committed("ncu_pipes_cdfdiff.json")
+            if pipes:                                          # MUFU thread-ops per launch counted from SASS by ncu at this very shape
+                e = pipes[0]
+                if e.get("registers") == _regs("bottleneck_fwd_kernel<3,1,3,0>"):
+                    peak_mufu = 148 * 16 * 1.965e9
+                    row.update({"mufu_thread_ops_per_launch": e["mufu_thread_ops"], "mufu_ops_per_s": e["mufu_thread_ops"] / t,
+                                "mufu_peak_ops_per_s": peak_mufu, "mufu_frac_of_peak": e["mufu_thread_ops"] / t / peak_mufu,
+                                "warp_inst_per_launch": e["warp_inst"], "issue_frac_of_peak": e["warp_inst"] / t / (148 * 4 * 1.965e9),
+                                "counts_source": "profiles/ncu_pipes_cdfdiff.json (ncu SASS page, same register allocation)"})
+            out["k1_fwd_cdfdiff_sweep_top"] = row
         del yl
     # G3 (north_star's tensor-core contraction; not on the default step, which runs the reference's diagonal GDN): pipelined
-    # tcgen05 kernel at the same site shape
-    if N in (32, 64, 96, 128, 192):
-        xd = torch.randn(B if N <= 128 else max(B // 2, 1), N, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
-        gm = torch.sqrt(torch.rand(N, N, device=dev) * 0.02 + torch.eye(N, device=dev) * 0.1 + 2.0 ** -18)
-        bd = torch.sqrt(torch.rand(N, device=dev) + 0.5)
+    # tcgen05 kernel at the largest site shape, C = 128 (the N=128 model) and C = 192 (the N=192 model of cfg4)
+    for Cd, Bd in ((128, 16), (192, 8)):
+        xd = torch.randn(Bd, Cd, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
+        gm = torch.sqrt(torch.rand(Cd, Cd, device=dev) * 0.02 + torch.eye(Cd, device=dev) * 0.1 + 2.0 ** -18)
+        bd = torch.sqrt(torch.rand(Cd, device=dev) + 0.5)
         t = time_it(lambda: F.gdn_dense(xd, bd, gm, False))
         nd = xd.numel()
-        out["gdn_dense_fwd_tcgen05"] = {"shape": list(xd.shape), "bytes": 8 * nd, "ms": t * 1e3, "gbs": 8 * nd / t / 1e9,
-                                        "tf32_mma_tflops": 4.0 * N * nd / t / 1e12}
-        del xd
+        out[f"gdn_dense_fwd_tcgen05_c{Cd}"] = {"shape": list(xd.shape), "bytes": 8 * nd, "ms": t * 1e3, "gbs": 8 * nd / t / 1e9,
+                                               "tf32_mma_tflops": 4.0 * Cd * nd / t / 1e12}
+        xr, br, gr = xd.clone().requires_grad_(True), bd.clone().requires_grad_(True), gm.clone().requires_grad_(True)
+        yv = F.gdn_dense(xr, br, gr, False)
+        go = torch.randn_like(yv)
+        t = time_it(lambda: torch.autograd.grad(yv, (xr, br, gr), go, retain_graph=True), reps=5)
+        out[f"gdn_dense_bwd_tcgen05_c{Cd}"] = {"shape": list(xd.shape), "bytes": 12 * nd, "ms": t * 1e3, "gbs": 12 * nd / t / 1e9,
+                                               "note": "dx, d(beta), d(gamma): all launches of the backward"}
+        del xd, xr, yv, go
     for v in out.values():
         v["frac_of_hbm_peak"] = v["gbs"] / peak
     # The dominant own kernel of the step is the GDN backward at the largest site, in the layout the step actually runs
     # (channels_last by default -> gdn_bwd_nhwc_kernel; --nchw -> gdn_bwd_kernel).  `traffic` = dram__bytes_read.sum +
-    # dram__bytes_write.sum of that kernel at this shape from the committed ncu --set full capture
-    # (profiles/r01_ncu_kernels_final.txt); only meaningful for the cfg2 site shape.
+    # dram__bytes_write.sum of that kernel at this shape, looked up in profiles/ncu_traffic.json (written by scripts/ncu_traffic.py
+    # from a committed ncu --set full capture) and used ONLY if the capture's registers/thread equal those of the loaded library.
     if channels_last:
-        dom, kname = out["gdn_bwd_channels_last"], "gdn_bwd_nhwc_kernel (GDN backward, channels_last) at the largest site of the step"
-        traffic = 1.073845e9 + 0.501128e9 if (B, N) == (16, 128) else None
+        dom, kid = out["gdn_bwd_channels_last"], "gdn_bwd_nhwc_kernel<0>"
+        kname = "gdn_bwd_nhwc_kernel (GDN backward, channels_last) at the largest site of the step"
     else:
-        dom, kname = out["gdn_bwd"], "gdn_bwd_kernel (GDN backward, NCHW) at the largest site of the step"
-        traffic = 1.0737e9 + 0.4981e9 if (B, N) == (16, 128) else None
+        dom, kid = out["gdn_bwd"], "gdn_bwd_kernel<0,1>"
+        kname = "gdn_bwd_kernel (GDN backward, NCHW) at the largest site of the step"
+    traffic, tsrc = None, None
+    regs = _regs(kid)
+    for e in _committed("ncu_traffic.json") or []:
+        if e["kernel"] == kid and e["shape"] == dom["shape"] and e["registers"] == regs:
+            traffic = e["dram_read_bytes"] + e["dram_write_bytes"]
+            tsrc = f"profiles/ncu_traffic.json <- {e['capture']} ({kid}, {regs} registers/thread: matches the loaded library)"
     roof = {"kernel": kname, "bound": "hbm", "achieved": dom["gbs"], "peak": peak,
-            "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01_ncu_kernels_final.txt",
-            "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"]}
+            "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic, "traffic_source": tsrc, "registers_per_thread": regs,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"],
+            "timing": "CUDA events on the launching stream around the whole backward of the site (main kernel + the per-channel "
+                      "finalize), L2 flushed before each of 10 repetitions, a queued spin lets the host run ahead; median"}
     return roof, out
+
+
+def _committed(name):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", name)))
+    except (OSError, ValueError):
+        return None
+
+
+def _regs(kernel_id):
+    from domain_specific_image_compression_b200 import _lib
+    r = _lib.load().sic_kernel_registers(kernel_id.encode())
+    return r if r > 0 else None
 
 
 def main():

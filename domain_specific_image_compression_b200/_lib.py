@@ -26,6 +26,9 @@ _z = ctypes.c_size_t
 PROTOTYPES = {
     "sic_version": (_i, []),
     "sic_last_error": (ctypes.c_char_p, []),
+    "sic_kernel_count": (_i, []),
+    "sic_kernel_name": (ctypes.c_char_p, [_i]),
+    "sic_kernel_registers": (_i, [ctypes.c_char_p]),
     "sic_bottleneck_workspace_bytes": (_z, [_i, _i, _i]),
     "sic_bottleneck_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "sic_bottleneck_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
@@ -36,6 +39,8 @@ PROTOTYPES = {
     "sic_gdn_dense_fwd_variant": (_i, [_p, _p, _p, _l, _i, _i, _p, _i, _p]),
     "sic_gdn_dense_bwd_part_rows": (_i, [_l, _i]),
     "sic_gdn_dense_bwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _i, _p]),
+    "sic_gdn_dense_dgamma_workspace_bytes": (_z, [_l, _i]),
+    "sic_gdn_dense_dgamma": (_i, [_p, _p, _l, _i, _p, _p, _z, _p]),
     "sic_ssim_tiles": (_l, [_i, _i]),
     "sic_ssim_fwd": (_i, [_p, _p, _i, _i, _i, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p]),
     "sic_ssim_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),

@@ -30,6 +30,7 @@ SOURCES = [
     ("gdn_dense.cu", []),
     ("gdn_dense_ws.cu", []),
     ("gdn_dense_bwd.cu", []),
+    ("gdn_dense_dgamma.cu", []),
     ("msssim.cu", []),
     ("tables.cu", ["-fmad=false"]),
     ("rans_host.cpp", []),

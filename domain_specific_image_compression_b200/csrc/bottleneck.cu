@@ -37,6 +37,12 @@ int bottleneck_cdfdiff_bwd(const float *y_tilde, const float *mu, const float *s
                            float *dy, float *dmu, float *dsigma, float *dnu, void *workspace, size_t workspace_bytes,
                            cudaStream_t st);
 
+SIC_REGISTER_KERNEL("bottleneck_fwd_kernel<0,1,3,0>", bottleneck_fwd_kernel<MODE_T_BCAST, true, SIC_QUANT_NOISE_PHILOX, false>);
+SIC_REGISTER_KERNEL("bottleneck_fwd_kernel<0,1,1,0>", bottleneck_fwd_kernel<MODE_T_BCAST, true, SIC_QUANT_ROUND, false>);
+SIC_REGISTER_KERNEL("bottleneck_fwd_kernel<1,1,3,0>", bottleneck_fwd_kernel<MODE_T_SPATIAL, true, SIC_QUANT_NOISE_PHILOX, false>);
+SIC_REGISTER_KERNEL("bottleneck_fwd_kernel<2,1,3,0>", bottleneck_fwd_kernel<MODE_GAUSS, true, SIC_QUANT_NOISE_PHILOX, false>);
+SIC_REGISTER_KERNEL("bottleneck_bwd_kernel<0,1>", bottleneck_bwd_kernel<MODE_T_BCAST, true>);
+SIC_REGISTER_KERNEL("bottleneck_bwd_kernel<1,1>", bottleneck_bwd_kernel<MODE_T_SPATIAL, true>);
 }  // namespace sic
 
 using namespace sic;

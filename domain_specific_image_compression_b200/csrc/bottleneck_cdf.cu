@@ -8,6 +8,9 @@ namespace {
 inline bool al16(const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 }  // namespace
 
+SIC_REGISTER_KERNEL("bottleneck_fwd_kernel<3,1,3,0>", bottleneck_fwd_kernel<MODE_CDF_BCAST, true, SIC_QUANT_NOISE_PHILOX, false>);
+SIC_REGISTER_KERNEL("bottleneck_bwd_kernel<3,1>", bottleneck_bwd_kernel<MODE_CDF_BCAST, true>);
+
 int bottleneck_cdfdiff_fwd(const float *y, const float *noise, uint64_t *philox, const float *mu, const float *sigma,
                            const float *nu, int B, int C, int HW, int quant_mode, int param_layout, float *y_tilde, float *nll,
                            float *bits, void *workspace, size_t workspace_bytes, cudaStream_t st) {

@@ -72,6 +72,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // 23 random bits -> odd multiple of 2^-24 in (-1/2, 1/2): symmetric, never exactly +-1/2, every step exact in fp32
 __device__ __forceinline__ float u32_to_noise(uint32_t r) { return ((float)(r >> 9) + 0.5f) * 1.1920928955078125e-07f - 0.5f; }
 
+// Registry of the hot kernels (name -> function) behind sic_kernel_registers(): lets the bench check that a committed ncu
+// capture (profiles/) describes the binary that is actually loaded (same register allocation) before quoting its DRAM traffic.
+void register_kernel(const char *name, const void *fn);
+struct KernelReg {
+    KernelReg(const char *name, const void *fn) { register_kernel(name, fn); }
+};
+#define SIC_CAT2(a, b) a##b
+#define SIC_CAT(a, b) SIC_CAT2(a, b)
+#define SIC_REGISTER_KERNEL(name, ...) static ::sic::KernelReg SIC_CAT(sic_kernel_reg_, __LINE__)(name, (const void *)(__VA_ARGS__))
+
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {

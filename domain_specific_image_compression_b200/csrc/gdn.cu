@@ -357,6 +357,15 @@ inline int bwd_chunks(int HW) {
     return (HW + per - 1) / per;
 }
 
+SIC_REGISTER_KERNEL("gdn_fwd_vec_kernel<0>", gdn_fwd_vec_kernel<false>);
+SIC_REGISTER_KERNEL("gdn_fwd_vec_kernel<1>", gdn_fwd_vec_kernel<true>);
+SIC_REGISTER_KERNEL("gdn_fwd_nhwc_kernel<0>", gdn_fwd_nhwc_kernel<false>);
+SIC_REGISTER_KERNEL("gdn_fwd_nhwc_kernel<1>", gdn_fwd_nhwc_kernel<true>);
+SIC_REGISTER_KERNEL("gdn_bwd_kernel<0,1>", gdn_bwd_kernel<false, true>);
+SIC_REGISTER_KERNEL("gdn_bwd_kernel<1,1>", gdn_bwd_kernel<true, true>);
+SIC_REGISTER_KERNEL("gdn_bwd_nhwc_kernel<0>", gdn_bwd_nhwc_kernel<false>);
+SIC_REGISTER_KERNEL("gdn_bwd_nhwc_kernel<1>", gdn_bwd_nhwc_kernel<true>);
+
 }  // namespace
 }  // namespace sic
 

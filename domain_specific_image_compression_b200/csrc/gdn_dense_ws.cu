@@ -311,6 +311,11 @@ int launch_dense_ws(const float *x, const float *beta_param, const float *gamma_
     return 0;
 }
 
+SIC_REGISTER_KERNEL("gdn_dense_ws_kernel<128,0>", gdn_dense_ws_kernel<128, false>);
+SIC_REGISTER_KERNEL("gdn_dense_ws_kernel<128,1>", gdn_dense_ws_kernel<128, true>);
+SIC_REGISTER_KERNEL("gdn_dense_ws_kernel<192,0>", gdn_dense_ws_kernel<192, false>);
+SIC_REGISTER_KERNEL("gdn_dense_ws_kernel<192,1>", gdn_dense_ws_kernel<192, true>);
+
 }  // namespace
 
 int gdn_dense_ws_dispatch(const float *x, const float *beta_param, const float *gamma_param, long positions, int C, int inverse,

@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(kThreads) ssim_bwd_kernel(const float *__restr
     }
 }
 
+SIC_REGISTER_KERNEL("ssim_fwd_kernel", ssim_fwd_kernel);
+SIC_REGISTER_KERNEL("ssim_bwd_kernel", ssim_bwd_kernel);
 }  // namespace
 }  // namespace sic
 

@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(kWarps * 32) rans_decode_kernel(const uint8_t 
     if (lane == 0) status[s] = trunc ? SIC_E_TRUNCATED : (corrupt ? SIC_E_CORRUPT : 0);
 }
 
+SIC_REGISTER_KERNEL("rans_encode_kernel", rans_encode_kernel);
+SIC_REGISTER_KERNEL("rans_decode_kernel", rans_decode_kernel);
 }  // namespace
 }  // namespace sic
 

@@ -305,6 +305,9 @@ __global__ void __launch_bounds__(256) symbols_kernel(const float *__restrict__ 
     }
 }
 
+SIC_REGISTER_KERNEL("cdf_tables_kernel", cdf_tables_kernel);
+SIC_REGISTER_KERNEL("minmax_kernel", minmax_kernel);
+SIC_REGISTER_KERNEL("symbols_kernel", symbols_kernel);
 }  // namespace
 }  // namespace sic
 

@@ -270,8 +270,9 @@ def gdn(x: torch.Tensor, beta_param: torch.Tensor, gamma_weight: torch.Tensor, i
 
 
 class _GDNDense(torch.autograd.Function):
-    """Dense-gamma GDN (G3).  Forward: the tcgen05 kernel.  Backward: the two GEMMs of SURVEY 8(a') G3 through torch.matmul
-    (plain library GEMMs, cuBLAS) on the re-parameterised gamma — the dense path is a capability the reference never runs."""
+    """Dense-gamma GDN (G3), forward and backward on tcgen05 tensor cores.  Backward (SURVEY 8(a') G3) = three launches of
+    libsic.so: pass 1 (s, h, direct, d(beta) partials), pass 2 (dx = direct + 2 x gamma^T h), pass 3 (d(gamma) = h^T x^2).
+    The dense path is a capability the reference stores parameters for (layers.py:13) but never runs."""
 
     @staticmethod
     @_amp_fwd
@@ -300,51 +301,28 @@ class _GDNDense(torch.autograd.Function):
     @staticmethod
     @_amp_bwd
     def backward(ctx, g):
-        xc, beta_param, gamma_param = ctx.saved_tensors
-        B, C, H, W = xc.shape
-        if os.environ.get("SIC_DENSE_BWD") == "1":
-            return _GDNDense._backward_fused(ctx, g, xc, beta_param, gamma_param)
-        X = xc.permute(0, 2, 3, 1).reshape(-1, C)                    # [P, C] view of the channels-last block
-        G = g.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(-1, C)
-        beta = beta_param * beta_param - 2.0 ** -18
-        gamma = gamma_param * gamma_param - 2.0 ** -18
-        X2 = X * X
-        s = torch.addmm(beta, X2, gamma.t())                         # s[p,i] = beta_i + sum_j gamma_ij x2[p,j]
-        d = torch.sqrt(s)
-        if ctx.inverse:
-            h = 0.5 * G * X / d
-            direct = G * d
-        else:
-            h = -0.5 * G * X / (d * s)
-            direct = G / d
-        dX = direct + 2.0 * X * (h @ gamma)                          # dx_j = direct_j + 2 x_j sum_i gamma_ij h_i
-        dgamma = h.t() @ X2                                          # dgamma_ij = sum_p h_i x2_j
-        dbeta = h.sum(0)
-        dx = dX.reshape(B, H, W, C).permute(0, 3, 1, 2)
-        return dx, dbeta * 2.0 * beta_param, dgamma * 2.0 * gamma_param, None, None
-
-
-    @staticmethod
-    def _backward_fused(ctx, g, xc, beta_param, gamma_param):
-        """Opt-in (SIC_DENSE_BWD=1): the two-pass tcgen05 backward of csrc/gdn_dense_bwd.cu — dx, h and the d(beta) partials come
-        from the kernels, d(gamma) = h^T x^2 stays a library GEMM.  Not device-tested yet (see include/sic.h)."""
         lib = _lib.load()
+        xc, beta_param, gamma_param = ctx.saved_tensors
         B, C, H, W = xc.shape
         P = B * H * W
         gc = _dense_layout(g.contiguous(memory_format=torch.channels_last), "grad_output")[0]
         h, direct, dx = torch.empty_like(xc), torch.empty_like(xc), torch.empty_like(xc)
         rows = lib.sic_gdn_dense_bwd_part_rows(P, C)
         part = torch.empty((rows, C), dtype=torch.float32, device=xc.device)
+        dgamma = torch.empty((C, C), dtype=torch.float32, device=xc.device)
+        nws = lib.sic_gdn_dense_dgamma_workspace_bytes(P, C)
+        ws = _workspace(xc.device, nws, "scratch")
+        global launch_count
         with torch.cuda.device(xc.device):
             _lib.check(lib.sic_gdn_dense_bwd(_ptr(xc), _ptr(gc), _ptr(beta_param), _ptr(gamma_param), P, C, int(ctx.inverse), _ptr(h),
                                              _ptr(direct), _ptr(dx), _ptr(part), rows, _stream()), "sic_gdn_dense_bwd")
-        global launch_count
-        launch_count += 2
-        X = xc.permute(0, 2, 3, 1).reshape(-1, C)
-        Hm = h.permute(0, 2, 3, 1).reshape(-1, C)
-        dgamma = Hm.t() @ (X * X)                                   # d(gamma_eff)_ij = sum_p h_i x_j^2
-        dbeta = part.sum(0)
-        return dx, dbeta * 2.0 * beta_param, dgamma * 2.0 * gamma_param, None, None
+            launch_count += 2
+            if ctx.needs_input_grad[2]:
+                _lib.check(lib.sic_gdn_dense_dgamma(_ptr(xc), _ptr(h), P, C, _ptr(dgamma), _ptr(ws), ws.numel(), _stream()),
+                           "sic_gdn_dense_dgamma")
+                launch_count += 2
+        dbeta = part.sum(0)                                          # fixed-order fold of the per-CTA partial rows
+        return dx, dbeta * 2.0 * beta_param, (dgamma * 2.0 * gamma_param if ctx.needs_input_grad[2] else None), None, None
 
 
 def gdn_dense(x: torch.Tensor, beta_param: torch.Tensor, gamma_param: torch.Tensor, inverse: bool = False,

@@ -1,12 +1,16 @@
-"""Data-parallel training step: one process per GPU, flat gradient bucket, one NCCL all-reduce per step.
+"""Data-parallel training step: one process per GPU, flat gradient buffer, bucketed NCCL all-reduce overlapped with backward.
 
 The reference trains on a single GPU (train.py:191-204: zero_grad, forward 'noise', loss, backward, clip 1.0, Adam) and has
 no distributed code at all.  Patches are independent, so the B200 design is pure data parallelism over the
 NVSwitch domain: every rank holds a full replica (26-60 MB of weights), runs the reference's step on its own patches, and
 the only exchange is the gradient all-reduce.  The parameters live in ONE flat fp32 buffer (the modules' tensors are views
 into it) so that
-  - the all-reduce is a single ncclAllReduce over 25.9 MB (N=128,M=192) / 59.8 MB (N=192,M=320): launch-latency bound on
-    NVLink 5, in-switch reduction (NVLS) when NCCL enables it;
+  - the gradients are reduced in place in ONE flat buffer (25.9 MB for N=128,M=192; 59.8 MB for N=192,M=320) cut into a few
+    contiguous buckets in reverse parameter order; each bucket's ncclAllReduce is issued (asynchronously, on NCCL's stream)
+    from an autograd hook the moment its last gradient exists, so it runs under the rest of the backward pass — g_s and the
+    hyper networks finish first and the 256^2 / 128^2 analysis sites that follow take milliseconds.  Only the last, small
+    bucket (the first analysis layers) is exposed.  Round 1 issued one all-reduce after backward() had returned: 7.04 -> 7.20
+    ms per step at 8 GPUs with nothing left to hide it under;
   - global-norm clipping and Adam are three launches on the flat buffer instead of ~80 per-tensor launch groups;
   - the dead parameters (per GDN site: the CxC `gamma` on the reference's diagonal path, layers.py:13; `gamma_conv.weight`
     when the site runs dense) are simply left out of the bucket — plain
@@ -48,7 +52,7 @@ def _is_dense_permutation(p: torch.Tensor) -> bool:
 class FlatTrainer:
     def __init__(self, module: torch.nn.Module, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, grad_clip: float = 1.0, process_group=None, fused: Optional[bool] = None,
-                 exclude: Iterable[str] = ()):
+                 exclude: Iterable[str] = (), bucket_bytes: int = 6 << 20):
         self.module = module
         self.grad_clip = grad_clip
         self.group = process_group
@@ -60,14 +64,16 @@ class FlatTrainer:
         total = sum(p.numel() for p in self.live)
         ref = self.live[0]
         self.flat = torch.empty(total, dtype=ref.dtype, device=ref.device)
-        off = 0
+        offsets, off = [], 0
         for p in self.live:                    # re-seat every parameter as a view into the flat buffer
             n = p.numel()
             view = self.flat[off:off + n].as_strided(p.size(), p.stride()) if _is_dense_permutation(p) else self.flat[off:off + n].view_as(p)
             view.copy_(p.detach())             # keeps a channels_last weight channels_last inside the flat buffer
             p.data = view
+            offsets.append(off)
             off += n
         self.flat.requires_grad_(True)
+        self.flat_grad = torch.zeros_like(self.flat)              # persistent: what the all-reduces and Adam work on
         if self.world > 1:                     # identical replicas: rank 0's weights win
             dist.broadcast(self.flat.detach(), src=0, group=process_group)
         if fused is None:
@@ -77,18 +83,60 @@ class FlatTrainer:
                                     capturable=bool(self.flat.is_cuda))
         self.graph = None
         self.nbytes_allreduce = total * self.flat.element_size()
+        # Buckets: contiguous slices of the flat buffer, formed walking the parameters BACKWARDS (the order backward() roughly
+        # produces gradients in) and closed once they hold bucket_bytes.  (lo, hi, first_param, last_param + 1)
+        self.buckets = []
+        hi_i, acc = len(self.live), 0
+        for i in range(len(self.live) - 1, -1, -1):
+            acc += self.live[i].numel() * self.flat.element_size()
+            if acc >= bucket_bytes or i == 0:
+                lo = offsets[i]
+                hi = offsets[hi_i - 1] + self.live[hi_i - 1].numel()
+                self.buckets.append((lo, hi, i, hi_i))
+                hi_i, acc = i, 0
+        self._bucket_of = {}
+        for k, (_, _, a, b) in enumerate(self.buckets):
+            for i in range(a, b):
+                self._bucket_of[id(self.live[i])] = k
+        self._pending = [0] * len(self.buckets)
+        self._works = []
+        self._armed = False
+        self.fire_order: List[int] = []        # bucket indices in the order their all-reduce was issued in the last step
+        for p in self.live:
+            p.register_post_accumulate_grad_hook(self._on_grad)
+
+    # ------------------------------------------------------------------------------------------------- gradient buckets
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        if not self._armed:
+            return
+        k = self._bucket_of[id(p)]
+        self._pending[k] -= 1
+        if self._pending[k] == 0:
+            self._fire(k)
+
+    def _fire(self, k: int) -> None:
+        """Every gradient of bucket k exists: pack them into the bucket's slice of the flat buffer and start its all-reduce."""
+        lo, hi, a, b = self.buckets[k]
+        torch.cat([_flat_in_param_order(self.live[i].grad, self.live[i]) for i in range(a, b)], out=self.flat_grad[lo:hi])
+        self.fire_order.append(k)
+        if self.world > 1:                     # asynchronous: runs on the collective's own stream under the rest of backward()
+            self._works.append(dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def pack_grads(self) -> torch.Tensor:
-        missing = [n for n, p in zip(self.names, self.live) if p.grad is None]
+        """The flat gradient once backward() has run (buckets already packed — and being reduced — by the hooks)."""
+        missing = [self.names[i] for k, (_, _, a, b) in enumerate(self.buckets) if self._pending[k] > 0
+                   for i in range(a, b) if self.live[i].grad is None]
         if missing:
             raise RuntimeError(f"parameters without gradient after backward: {missing[:4]}...")
-        return torch.cat([_flat_in_param_order(p.grad, p) for p in self.live])
+        return self.flat_grad
 
     def reduce_clip_step(self, flat_grad: torch.Tensor) -> torch.Tensor:
-        """all-reduce (mean) -> global-norm clip (torch.nn.utils.clip_grad_norm_ semantics, train.py:200-202) -> Adam.
-        Returns the pre-clip global gradient norm (device scalar, no host sync)."""
+        """wait for the bucket all-reduces (mean) -> global-norm clip (torch.nn.utils.clip_grad_norm_ semantics, train.py:200-202)
+        -> Adam.  Returns the pre-clip global gradient norm (device scalar, no host sync)."""
+        for w in self._works:                  # stream-level wait (the host does not block on CUDA)
+            w.wait()
+        self._works = []
         if self.world > 1:
-            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)
             flat_grad.mul_(1.0 / self.world)
         norm = torch.linalg.vector_norm(flat_grad)
         if self.grad_clip and self.grad_clip > 0:
@@ -101,13 +149,19 @@ class FlatTrainer:
         """loss_closure runs forward + loss on this rank's patches and returns the scalar loss."""
         for p in self.live:
             p.grad = None                      # zero_grad(set_to_none=True), train.py:195
-        loss = loss_closure()
-        loss.backward()
+        for k, (_, _, a, b) in enumerate(self.buckets):
+            self._pending[k] = b - a
+        self._works, self.fire_order, self._armed = [], [], True
+        try:
+            loss = loss_closure()
+            loss.backward()
+        finally:
+            self._armed = False
         self.reduce_clip_step(self.pack_grads())
         return loss.detach()
 
     def capture(self, loss_closure: Callable[[], torch.Tensor], warmup: int = 3) -> Callable[[], torch.Tensor]:
-        """Record zero_grad + forward + loss + backward + all-reduce + clip + Adam into ONE CUDA graph and return a
+        """Record zero_grad + forward + loss + backward + the bucket all-reduces + clip + Adam into ONE CUDA graph and return a
         replay function.  The closure must read its batch from a static tensor (copy the next batch into it before each
         replay).  The in-kernel Philox offset advances on the device, so every replay draws fresh quantisation noise.
         Launch-bound inner loops are what graphs are for: the step is ~600 small launches next to a dozen large ones."""
@@ -129,3 +183,76 @@ class FlatTrainer:
             graph.replay()
             return static_loss
         return replay
+
+    def release_graph(self) -> None:
+        """Drop the captured step (its NCCL kernels reference the communicator): call before destroy_process_group()."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+            for p in self.live:
+                p.grad = None
+
+
+class HostFedLoop:
+    """Feeds a (captured or eager) step from pinned HOST batches without stalling the device on the copies.
+
+    Per step: the batch goes host -> device on a copy stream into one of two landing buffers while the previous step is still
+    computing; the step stream waits for that copy, moves the 12.6 MB batch into the step's static input (device-to-device),
+    runs the step; the scalar loss goes device -> host on the copy stream and is handed back ONE STEP LATE, so the host never
+    blocks on the step it has just enqueued.  Every step still pays its own H2D and D2H; they are simply no longer serialised
+    with the kernels (round 1: blocking copy_ before and after the replay, 0.14 ms/step on one GPU, 0.50 ms at eight)."""
+
+    def __init__(self, run_step: Callable[[], torch.Tensor], x_static: torch.Tensor):
+        self.run_step, self.x_static = run_step, x_static
+        self.copy_stream = torch.cuda.Stream(device=x_static.device)
+        self.land = [torch.empty_like(x_static) for _ in range(2)]
+        self.loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+        self.d2h_done = [torch.cuda.Event() for _ in range(2)]
+        self.step_done = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+        self._staged = False
+
+    def stage(self, x_host: torch.Tensor) -> None:
+        """Start the host->device copy of the batch of the NEXT step() call."""
+        k = self.i % 2
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[k])          # the step that last read this landing buffer has moved it on
+            self.land[k].copy_(x_host, non_blocking=True)
+            self.h2d_done[k].record(self.copy_stream)
+        self._staged = True
+
+    def step(self, x_host_next: Optional[torch.Tensor] = None) -> Optional[float]:
+        """Runs one step on the staged batch, stages `x_host_next` for the following call, returns the PREVIOUS step's loss."""
+        if not self._staged:
+            raise RuntimeError("HostFedLoop.step: call stage(batch) first")
+        k = self.i % 2
+        main = torch.cuda.current_stream(self.x_static.device)
+        main.wait_event(self.h2d_done[k])
+        if self.i >= 1:
+            main.wait_event(self.d2h_done[(self.i - 1) % 2])        # the previous loss has left the static tensor the step rewrites
+        self.x_static.copy_(self.land[k], non_blocking=True)
+        self.consumed[k].record(main)
+        loss = self.run_step()
+        self.step_done[k].record(main)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.step_done[k])
+            self.loss_host[k].copy_(loss, non_blocking=True)
+            self.d2h_done[k].record(self.copy_stream)
+        self.i += 1
+        self._staged = False
+        if x_host_next is not None:
+            self.stage(x_host_next)
+        if self.i >= 2:
+            prev = (self.i - 2) % 2
+            self.d2h_done[prev].synchronize()                       # the loss of the step before the one just enqueued
+            return float(self.loss_host[prev])
+        return None
+
+    def drain(self) -> float:
+        """Loss of the last step (blocks until it is on the host)."""
+        last = (self.i - 1) % 2
+        self.d2h_done[last].synchronize()
+        return float(self.loss_host[last])

@@ -53,6 +53,13 @@ enum {
 int sic_version(void);
 const char *sic_last_error(void);
 
+/* Introspection of the loaded binary: the hot kernels by name (template arguments as ncu prints them, without spaces: "gdn_bwd_nhwc_kernel<0>", "bottleneck_bwd_kernel<0,1>", ...)
+ * and the registers per thread each was compiled to (cudaFuncGetAttributes).  bench.py uses it to quote the DRAM traffic of a
+ * committed ncu capture (profiles/) only when that capture is of the same register allocation as the library that is running. */
+int sic_kernel_count(void);
+const char *sic_kernel_name(int i);
+int sic_kernel_registers(const char *name);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * K1  fused quantise + likelihood + rate.   Replaces model.py:27-35 (quantize), distributions.py:20-31 / :39-46
  * (neg_log2_prob) and the two .sum() of model.py:77 (≈25 eager launches) with one launch.
@@ -121,12 +128,21 @@ int sic_gdn_dense_fwd_variant(const float *x, const float *beta_param, const flo
  *   contracts with x^2 for d(gamma_eff)_ij = sum_p h_i x_j^2, a plain library GEMM); dbeta_part [part_rows, C] with
  *   part_rows >= sic_gdn_dense_bwd_part_rows(positions, C): d(beta_eff) = column sums.  Gradients are w.r.t. the EFFECTIVE
  *   beta/gamma; the chain rule through the squared re-parameterisation (x 2 beta_param, x 2 gamma_param) is the caller's.
- *   gamma is consumed at TF32 precision as in the forward.  C in {32, 64, 96, 128, 192}.
- *   STATUS: compiled for sm_100a but not yet device-tested (written after the round's GPU budget was spent); the Python host
- *   only uses it when SIC_DENSE_BWD=1. */
+ *   gamma is consumed at TF32 precision as in the forward.  C in {32, 64, 96, 128, 192}.  Device-validated in round 2
+ *   (tests/test_gpu_gdn.py::test_dense_gdn_fused_backward_vs_float64, 10 shapes incl. ragged tails and C = 192) and the default
+ *   backward of GDN(dense=True). */
 int sic_gdn_dense_bwd_part_rows(long positions, int C);
 int sic_gdn_dense_bwd(const float *x, const float *g, const float *beta_param, const float *gamma_param, long positions, int C,
                       int inverse, float *h, float *direct, float *dx, float *dbeta_part, int part_rows, void *stream);
+
+/* G3 backward, third pass: d(gamma_eff)[i][j] = sum_p h[p][i] * x[p][j]^2 on tcgen05 (kind::tf32, both operands MN-major straight
+ * from the channels-last layout, exact hi/lo split of h and x^2, one TMEM accumulator for the whole kernel, per-CTA partials
+ * folded in a fixed order).  h is pass 1's output of sic_gdn_dense_bwd.  dgamma_eff [C, C] row i = output channel; the chain rule
+ * through gamma = gamma_param^2 - 2^-18 (x 2 gamma_param) is the caller's, as for sic_gdn_dense_bwd.  One streaming pass: 8 B/element.
+ * workspace: sic_gdn_dense_dgamma_workspace_bytes(positions, C) bytes, any content.  C in {32, 64, 96, 128, 192}. */
+size_t sic_gdn_dense_dgamma_workspace_bytes(long positions, int C);
+int sic_gdn_dense_dgamma(const float *x, const float *h, long positions, int C, float *dgamma_eff, void *workspace,
+                         size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * K4  symbols: eval_selfcontained_entropy.py:39-40,48 / :52-53,62 (per patch, no host sync).

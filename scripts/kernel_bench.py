@@ -103,16 +103,17 @@ if args.only in ("", "dense"):
                 report(f"{'igdn' if inv else 'gdn'}_dense_fwd tcgen05 nhwc {vname}", x.shape, 8 * n, t)
                 rows[-1]["tflops_tf32_2pass"] = 2 * 2 * N * N * (n // N) / t / 1e12
                 print(f"    -> {rows[-1]['tflops_tf32_2pass']:.1f} TFLOP/s of tf32 MMA work (hi+lo passes)")
-        # backward (12 B/elem algorithmic = read x, g; write dx).  Default path: cuBLAS GEMMs + elementwise through
-        # torch; SIC_DENSE_BWD=1 in the environment switches to the two-pass tcgen05 kernel (csrc/gdn_dense_bwd.cu).
+        # backward (12 B/elem algorithmic = read x, g; write dx): three tcgen05 launches (csrc/gdn_dense_bwd.cu passes
+        # 1 and 2, csrc/gdn_dense_dgamma.cu) that move 40 B/elem
         try:
             xr = x.clone().requires_grad_(True)
             br, gr = beta.clone().requires_grad_(True), gm.clone().requires_grad_(True)
             yv = F.gdn_dense(xr, br, gr, False)
             go = torch.randn_like(yv)
             t = time_it(lambda: torch.autograd.grad(yv, (xr, br, gr), go, retain_graph=True), reps=5)
-            path = "tcgen05 2-pass" if os.environ.get("SIC_DENSE_BWD") == "1" else "torch/cuBLAS"
-            report(f"gdn_dense_bwd {path}", x.shape, 12 * n, t)
+            report("gdn_dense_bwd tcgen05 3-pass", x.shape, 12 * n, t)
+            t = time_it(lambda: torch.autograd.grad(yv, (xr, br), go, retain_graph=True), reps=5)
+            report("gdn_dense_bwd tcgen05 (dx, dbeta only)", x.shape, 12 * n, t)
             del xr, yv, go
         except Exception as e:
             print(f"dense bwd: FAILED {e}", flush=True)

@@ -11,7 +11,6 @@ M = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launc
      "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
      "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
      "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
-     "SM_A.TriageCompute.sm__inst_executed_pipe_xu_realtime.avg.pct_of_peak_sustained_elapsed",
      "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
      "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct"]
 print(f"# {rep}: ncu --set full --clock-control none (cold-cache, serialised replays: compare shares, not absolutes)")

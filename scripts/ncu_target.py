@@ -43,5 +43,34 @@ if which in ("dense192",):
     gm = torch.sqrt(torch.rand(192, 192, device=dev) * 0.02 + torch.eye(192, device=dev) * 0.1 + 2.0 ** -18)
     for _ in range(reps):
         F.gdn_dense(x, beta, gm, False)
+if which in ("cdf",):
+    y = torch.randn(16, 320, 128, 128, device=dev) * 3
+    sg = torch.exp(torch.randn(16, 320, 1, 1, device=dev)); nu = torch.exp(torch.randn(16, 320, 1, 1, device=dev) + 1.5)
+    for _ in range(reps):
+        F.bottleneck(y, sg, nu, quant="noise", lik="cdf_diff")
+if which in ("dense_bwd",):
+    for C, B in ((128, 16), (192, 8)):
+        x = torch.randn(B, C, 256, 256, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        beta = torch.sqrt(torch.rand(C, device=dev) + 0.5).requires_grad_(True)
+        gm = torch.sqrt(torch.rand(C, C, device=dev) * 0.02 + torch.eye(C, device=dev) * 0.1 + 2.0 ** -18).requires_grad_(True)
+        for _ in range(reps):
+            yv = F.gdn_dense(x, beta, gm, False)
+            torch.autograd.grad(yv, (x, beta, gm), torch.randn_like(yv))
+        del x, yv
+if which in ("codec",):
+    import domain_specific_image_compression_b200 as sic
+    torch.manual_seed(0)
+    m = sic.CompressionModel(N=128, M=192, min_nu=2.0).to(dev).eval()
+    with torch.no_grad():
+        m.g_a.g_a[14].weight.mul_(40.0); m.h_a.h_a[6].weight.mul_(40.0); m.h_s.mlp_nu[2].bias.add_(1.5)
+    xi = torch.rand(16, 3, 512, 512, device=dev)
+    for _ in range(reps):
+        comp = m.compress(xi)
+        m.decompress(comp)
+if which in ("ssim",):
+    from domain_specific_image_compression_b200 import losses
+    a = torch.rand(16, 3, 256, 256, device=dev, requires_grad=True); b = torch.rand(16, 3, 256, 256, device=dev)
+    for _ in range(reps):
+        losses.multi_scale_ssim(a, b, 1.0, torch.tensor([0.3, 0.5, 0.2], device=dev)).backward()
 torch.cuda.synchronize()
 print("ok")

@@ -293,15 +293,13 @@ def test_fused_conv_bias_is_bit_exact_and_returns_bias_gradient(fmt, inverse):
     assert float((ga[3] - ga[0].sum(dim=(0, 2, 3))).abs().max()) <= 1e-5 * float(ga[3].abs().max()) + 1e-6
 
 
-# ------------------------------------------------------------------------------ G3 backward on tcgen05 (opt-in, not yet device-tested)
-@pytest.mark.skipif(os.environ.get("SIC_EXPERIMENTAL") != "1",
-                    reason="csrc/gdn_dense_bwd.cu was written after the round's GPU budget ran out; run with SIC_EXPERIMENTAL=1 to validate it")
+# ------------------------------------------------------------------------------ G3 backward on tcgen05 (three passes)
 @pytest.mark.parametrize("inverse", [False, True])
 @pytest.mark.parametrize("shape", [(2, 64, 9, 11), (1, 128, 24, 24), (2, 192, 10, 13), (1, 96, 5, 7), (1, 128, 148 * 3 + 1, 128)])
-def test_dense_gdn_fused_backward_vs_float64(shape, inverse, monkeypatch):
-    """Two-pass tcgen05 backward (sic_gdn_dense_bwd) against float64 autograd through F.conv2d(x^2, gamma, beta) with the
-    effective gamma truncated to TF32 (what both MMA passes consume).  dx tight; d(beta), d(gamma) through the same h."""
-    monkeypatch.setenv("SIC_DENSE_BWD", "1")
+def test_dense_gdn_fused_backward_vs_float64(shape, inverse):
+    """tcgen05 backward (sic_gdn_dense_bwd: s/h/direct, dx; sic_gdn_dense_dgamma: h^T x^2) against float64 autograd through
+    F.conv2d(x^2, gamma, beta) with the effective gamma truncated to TF32 (what the MMA passes that read gamma consume).
+    dx tight; d(beta), d(gamma) through the same h."""
     F = _F()
     B, C, H, W = shape
     gen = torch.Generator(device="cuda").manual_seed(C + H + inverse)
@@ -349,3 +347,29 @@ def test_channels_last_backward_full_rounds_and_tail_vs_nchw(inverse):
     assert float((dx_a - dx_b).abs().max()) <= 1e-5 * float(dx_a.abs().max())
     for a, bb in ((db_a, db_b), (dw_a, dw_b), (dbias_a, dbias_b)):
         assert float((a - bb).abs().max()) <= 1e-4 * float(a.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("C,P", [(32, 7), (64, 100), (96, 33), (128, 32 * 148 * 2 + 5), (192, 1000), (128, 65536)])
+def test_dense_dgamma_kernel_vs_float64(C, P):
+    """sic_gdn_dense_dgamma on its own: d(gamma)[i][j] = sum_p h[p][i] x[p][j]^2 with both operands consumed MN-major from the
+    natural channels-last layout.  Against float64; the hi/lo split keeps the error at fp32-accumulation level (a plain
+    truncating tf32 product is ~7e-4 off).  Shapes: fewer positions than one 32-row stage, ragged tails, several tiles per
+    persistent CTA, the two-block C = 192 path."""
+    import ctypes
+    from domain_specific_image_compression_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator(device="cuda").manual_seed(C + P)
+    x = torch.randn(P, C, device="cuda", generator=gen) * 1.5
+    h = torch.randn(P, C, device="cuda", generator=gen) * torch.rand(1, C, device="cuda", generator=gen)
+    out = torch.full((C, C), float("nan"), device="cuda")
+    nws = lib.sic_gdn_dense_dgamma_workspace_bytes(P, C)
+    ws = torch.empty(max(nws, 16), dtype=torch.uint8, device="cuda")
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    for _ in range(2):                                     # twice: the workspace needs no initialisation and no reset
+        rc = lib.sic_gdn_dense_dgamma(vp(x), vp(h), P, C, vp(out), vp(ws), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, lib.sic_last_error()
+    ref = h.double().t() @ (x.double() ** 2)
+    err = float((out.double() - ref).abs().max())
+    assert err <= 2e-6 * float(ref.abs().max()) + 1e-6, (err, float(ref.abs().max()))
+    assert lib.sic_gdn_dense_dgamma(vp(x), vp(h), P, 48, vp(out), vp(ws), ws.numel(), None) == -3       # SIC_E_UNSUPPORTED
+    assert lib.sic_gdn_dense_dgamma(vp(x), vp(h), P, C, vp(out), vp(ws), 0, None) == (-2 if nws else 0)  # SIC_E_WORKSPACE

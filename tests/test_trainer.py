@@ -47,6 +47,27 @@ def test_flat_trainer_equals_reference_step():
     assert m.a.weight.data_ptr() == tr.flat.data_ptr()
 
 
+def test_buckets_partition_the_flat_buffer_and_fire_in_backward_order():
+    """Reverse-order buckets: contiguous, disjoint, covering; with a small cap every layer is its own bucket and the hooks start
+    the later layer's reduction first (its gradients exist first).  One big bucket gives the same update."""
+    torch.manual_seed(1)
+    m1, m2 = Toy(), Toy()
+    m2.load_state_dict(m1.state_dict())
+    small = FlatTrainer(m1, lr=1e-2, fused=False, exclude=["gamma"], bucket_bytes=8)
+    big = FlatTrainer(m2, lr=1e-2, fused=False, exclude=["gamma"], bucket_bytes=1 << 30)
+    assert len(big.buckets) == 1 and len(small.buckets) == 4
+    spans = sorted((lo, hi) for lo, hi, _, _ in small.buckets)
+    assert spans[0][0] == 0 and spans[-1][1] == small.flat.numel() and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    x = torch.rand(2, 3, 8, 8)
+    for _ in range(2):
+        small.step(lambda: _loss(m1, x))
+        big.step(lambda: _loss(m2, x))
+    assert torch.equal(small.flat.detach(), big.flat.detach())
+    first_bucket_params = {small.names[i] for i in range(small.buckets[small.fire_order[0]][2], small.buckets[small.fire_order[0]][3])}
+    assert first_bucket_params <= {"b.weight", "b.bias"}            # the last layer's gradients are reduced first
+    assert sorted(small.fire_order) == [0, 1, 2, 3]
+
+
 def test_dead_parameters_follow_the_gdn_mode():
     """Per GDN site: the reference's diagonal path trains `gamma_conv.weight` and never touches the CxC `gamma` (layers.py:13,21);
     GDN(dense=True) trains `gamma` and never touches `gamma_conv.weight`.  The bucket must hold exactly the live ones."""
