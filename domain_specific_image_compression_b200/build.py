@@ -32,6 +32,7 @@ SOURCES = [
     ("gdn_dense_bwd.cu", []),
     ("gdn_dense_dgamma.cu", []),
     ("msssim.cu", []),
+    ("hyper_tail.cu", []),
     ("tables.cu", ["-fmad=false"]),
     ("rans_host.cpp", []),
     ("rans_device.cu", []),

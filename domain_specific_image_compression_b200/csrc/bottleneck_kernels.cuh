@@ -154,92 +154,70 @@ __device__ __forceinline__ float t_cdf_nll(float x, const TConst &c) {
 }
 
 
-// ---- warp-cooperative forward --------------------------------------------------------------------------------------------
-// The per-lane panel loop above leaves 20 of 32 lanes idle on average (ncu r01: 12.0 active threads per instruction): elements
-// near zero with a small sigma need 4+ panels, their neighbours one.  Here the panels of the 32 elements a warp holds are
-// pooled and dealt out 32 at a time.  That needs panel boundaries any lane can compute, so they are uniform in
-// s = asinh(t / sqrt(nu)) — the closed form of the marching rule (dt/ds = sqrt(nu + t^2)); calibrated in float64 against
-// scipy like the marching rule: worst relative error 2.8e-7 at 1.5/sqrt(nu+1) per panel.
-template <bool UNIFORM>
-__device__ __forceinline__ float warp_cdf_nll(float x, bool active, const TConst &c) {
-    __shared__ float s_part[kWarpsPerCta][32];
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    float *part = s_part[threadIdx.x >> 5];
-    const float lo = (x - 0.5f) * c.inv_sigma, hi = (x + 0.5f) * c.inv_sigma;
-    const bool one_sided = lo >= 0.f || hi <= 0.f;
-    // piece 0: [A0, B0] (one-sided bin, or the right half of a straddling bin); piece 1: [0, B1] (left half, mirrored)
-    const float A0 = one_sided ? (lo >= 0.f ? lo : -hi) : 0.f;
-    const float B0 = one_sided ? (lo >= 0.f ? hi : -lo) : hi;
-    const float B1 = one_sided ? 0.f : -lo;
-    const float eref = one_sided ? -c.B2 * __log2f(fmaf(A0 * A0, c.inv_nu, 1.0f)) : 0.f;
-    auto asinh_f = [](float u) { return __logf(u + sqrtf(fmaf(u, u, 1.0f))); };
-    const float sA0 = asinh_f(A0 * c.inv_rn), sB0 = asinh_f(B0 * c.inv_rn), sB1 = asinh_f(B1 * c.inv_rn);
-    int n0 = (int)fminf(fmaxf(ceilf((sB0 - sA0) * c.inv_ds), 1.0f), (float)kMaxPanels);
-    int n1 = one_sided ? 0 : (int)fminf(fmaxf(ceilf(sB1 * c.inv_ds), 1.0f), (float)kMaxPanels);
-    if (!active) { n0 = 0; n1 = 0; }
-    const float d0 = (sB0 - sA0) / (float)max(n0, 1), d1 = sB1 / (float)max(n1, 1);
-    const int T = n0 + n1;
-    int incl = T;
+// ---- warp-uniform forward -------------------------------------------------------------------------------------------------
+// History (profiles/): the per-lane marching loop above kept 12 of 32 lanes busy (panel counts differ inside a warp: elements
+// near zero with a small sigma need 4+ panels, their neighbours one).  Round 1's answer pooled the panels of a warp's 32 elements
+// and dealt them out 32 at a time: all lanes busy, but ncu (profiles/r02b_ncu_cdfdiff_pooled.txt) showed what the dealing costs -
+// 1824 M warp instructions for 84 M elements of which only 119 M are MUFU; ISETP/BRA/SHFL/BSYNC/SEL are another 500 M; 121
+// registers, 16 resident warps, MUFU pipe at 18 % of its peak rate: bound by instruction issue and latency, not by the SFU.
+// This version removes the control flow instead of balancing it:
+//   * the bin [lo, hi] is ONE interval in s = asinh(t / sqrt(nu)) (odd, monotonic; dt/ds = sqrt(nu + t^2), so equal steps in s are
+//     the marching rule's local-scale panels, and a bin that straddles zero needs no splitting);
+//   * every lane cuts ITS OWN interval into n equal s-steps, n = the largest count any lane of the warp (and any of the 4
+//     elements a lane holds) asks for: the panel loop has a warp-uniform trip count, no divergence, no shuffles, no shared
+//     memory.  Lanes that needed fewer panels get narrower ones (more accurate, never less).  In the broadcast layout all lanes
+//     of a warp share sigma and nu, so n is set by the element nearest zero and the excess is small;
+//   * 4 elements x 8 nodes per trip are 32 independent LG2/EX2 chains per lane: the latency the 16-warp occupancy could not hide.
+// Same calibration as before (float64 against scipy: <= 2.8e-7 relative at an s-step of 1.5/sqrt(nu+1), kMaxPanels cap).
+__device__ __forceinline__ float asinh_signed(float u) {
+    const float a = fabsf(u);
+    return copysignf(__logf(a + sqrtf(fmaf(a, a, 1.0f))), u);
+}
+
+template <int E>
+__device__ __forceinline__ void uniform_cdf_nll(const float (&x)[E], bool active, const TConst &c, float (&out)[E]) {
+    float s0[E], ds[E], t0[E], hi[E], eref[E], S[E];
+    int n = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int v = __shfl_up_sync(full, incl, o);
-        if (lane >= o) incl += v;
+    for (int e = 0; e < E; ++e) {
+        const float lo = (x[e] - 0.5f) * c.inv_sigma;
+        hi[e] = (x[e] + 0.5f) * c.inv_sigma;
+        const float near = fminf(fmaxf(0.0f, lo), hi[e]);              // where the density peaks inside the bin: the scaling reference
+        eref[e] = -c.B2 * __log2f(fmaf(near * near, c.inv_nu, 1.0f));
+        s0[e] = asinh_signed(lo * c.inv_rn);
+        ds[e] = asinh_signed(hi[e] * c.inv_rn) - s0[e];
+        n = max(n, (int)fminf(fmaxf(ceilf(ds[e] * c.inv_ds), 1.0f), (float)kMaxPanels));
+        t0[e] = lo;
+        S[e] = 0.0f;
     }
-    const int excl = incl - T;
-    const int total = __shfl_sync(full, incl, 31);
-    float S = 0.f;
-    for (int base = 0; base < total; base += 32) {
-        const int j = base + lane;
-        int own = 0;  // largest lane whose exclusive offset is <= j (lanes without panels share their successor's offset)
+    n = __reduce_max_sync(0xffffffffu, active ? n : 0);
+    const float inv_n = __fdividef(1.0f, (float)max(n, 1));
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            int cand = own + step;
-            int ev = __shfl_sync(full, excl, cand & 31);
-            if (cand < 32 && ev <= j) own = cand;
-        }
-        const int k = j - __shfl_sync(full, excl, own);
-        const int on0 = __shfl_sync(full, n0, own), on1 = __shfl_sync(full, n1, own);
-        const float oA0 = __shfl_sync(full, A0, own), osA0 = __shfl_sync(full, sA0, own), oB0 = __shfl_sync(full, B0, own);
-        const float od0 = __shfl_sync(full, d0, own), oB1 = __shfl_sync(full, B1, own), od1 = __shfl_sync(full, d1, own);
-        const float oeref = __shfl_sync(full, eref, own);
-        float inv_nu = c.inv_nu, B2 = c.B2, rn = c.rn;
-        if (!UNIFORM) {
-            inv_nu = __shfl_sync(full, c.inv_nu, own);
-            B2 = __shfl_sync(full, c.B2, own);
-            rn = __shfl_sync(full, c.rn, own);
-        }
-        float I = 0.f;
-        if (j < total) {
-            const bool second = k >= on0;
-            const int kk = second ? k - on0 : k, np = second ? on1 : on0;
-            const float A = second ? 0.f : oA0, sA = second ? 0.f : osA0, B = second ? oB1 : oB0, d = second ? od1 : od0;
-            auto bound = [&](int idx) {   // exact ends, closed form inside: the same expression for both neighbours of a boundary
-                if (idx == 0) return A;
-                if (idx == np) return B;
-                float e = __expf(fmaf((float)idx, d, sA));
-                return rn * 0.5f * (e - __fdividef(1.0f, e));
-            };
-            const float t0 = bound(kk), t1 = bound(kk + 1);
-            const float m = 0.5f * (t0 + t1), h = 0.5f * (t1 - t0);
-            float acc = 0.f;
+    for (int e = 0; e < E; ++e) ds[e] *= inv_n;
+    for (int k = 1; k <= n; ++k) {                                     // warp-uniform trip count
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            float t1 = hi[e];                                          // exact ends; closed form inside
+            if (k < n) {
+                const float ex = __expf(fmaf((float)k, ds[e], s0[e]));
+                t1 = c.rn * 0.5f * (ex - __fdividef(1.0f, ex));
+            }
+            const float m = 0.5f * (t0[e] + t1), h = 0.5f * (t1 - t0[e]);
+            float acc = 0.0f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
 #pragma unroll
                 for (int sgn = -1; sgn <= 1; sgn += 2) {
                     float l2, w;
-                    acc = fmaf(kGLw[i], t_fs(fmaf(h, sgn * kGLx[i], m), inv_nu, B2, oeref, l2, w), acc);
+                    acc = fmaf(kGLw[i], t_fs(fmaf(h, sgn * kGLx[i], m), c.inv_nu, c.B2, eref[e], l2, w), acc);
                 }
             }
-            I = h * acc;
+            S[e] = fmaf(h, acc, S[e]);
+            t0[e] = t1;
         }
-        part[lane] = I;
-        __syncwarp();
-        const int j_begin = max(excl, base), j_end = min(incl, base + 32);   // my own panels inside this deal, in order
-        for (int jj = j_begin; jj < j_end; ++jj) S += part[jj - base];
-        __syncwarp();
     }
-    return active ? -(c.lc2 + eref + __log2f(S)) : 0.f;
+#pragma unroll
+    for (int e = 0; e < E; ++e) out[e] = active ? -(c.lc2 + eref[e] + __log2f(S[e])) : 0.0f;
 }
 
 struct GConst {
@@ -260,14 +238,19 @@ __device__ __forceinline__ float quantize1(float y, int quant_mode, float noise)
     return y;
 }
 
-// `active`: whether this lane holds a real element.  The cdf_diff modes are warp-cooperative, so every lane of the warp must
-// make the call (inactive lanes contribute no panels); the other modes ignore the flag.
+// `active`: whether this lane holds a real element.  The cdf_diff modes take a warp-wide maximum of the panel count, so every
+// lane of the warp must make the call (inactive lanes ask for no panels); the other modes ignore the flag.
 template <int MODE>
 __device__ __forceinline__ float elem_nll(float x, bool active, const TConst &tc, const GConst &gc, float sg, float nu) {
     if (MODE == MODE_GAUSS) return fmaf(gc.Bc, x * x, gc.A);
     if (MODE == MODE_T_SPATIAL) return t_nll(x, t_const(sg, nu));
-    if (MODE == MODE_CDF_SPATIAL) return warp_cdf_nll<false>(x, active, t_const(active ? sg : 1.0f, active ? nu : 4.0f));
-    if (MODE == MODE_CDF_BCAST) return warp_cdf_nll<true>(x, active, tc);
+    if (is_cdf(MODE)) {
+        const float xs[1] = {x};
+        float r[1];
+        if (MODE == MODE_CDF_SPATIAL) uniform_cdf_nll<1>(xs, active, t_const(active ? sg : 1.0f, active ? nu : 4.0f), r);
+        else uniform_cdf_nll<1>(xs, active, tc, r);
+        return r[0];
+    }
     return t_nll(x, tc);
 }
 
@@ -297,7 +280,7 @@ __device__ __forceinline__ bool retire_and_check_last(unsigned int *ticket) {
 // QUANT and HAS_MU are compile-time so that the prefetch registers of unused optional inputs (noise tensor, mu map)
 // disappear: the common training instance (broadcast, Philox, no mu) must stay <= 64 registers for 4 CTAs per SM.
 template <int MODE, bool VEC, int QUANT, bool HAS_MU>
-__global__ void __launch_bounds__(kThreads, is_cdf(MODE) ? 2 : 4) bottleneck_fwd_kernel(
+__global__ void __launch_bounds__(kThreads, is_cdf(MODE) ? 3 : 4) bottleneck_fwd_kernel(
     const float *__restrict__ y, const float *__restrict__ noise, uint64_t *__restrict__ philox,
     const float *__restrict__ mu_in, const float *__restrict__ sigma, const float *__restrict__ nu, Shape sh,
     int mu_layout, float *__restrict__ y_tilde, float *__restrict__ nll, float *__restrict__ bits, float *__restrict__ psum,
@@ -327,7 +310,9 @@ __global__ void __launch_bounds__(kThreads, is_cdf(MODE) ? 2 : 4) bottleneck_fwd
         }
         float acc = 0.0f;
         if (VEC) {
-            constexpr int U = is_spatial(MODE) ? 2 : 4;  // vectors in flight per lane (spatial mode streams 3 tensors)
+            // vectors in flight per lane (spatial mode streams 3 tensors; the cdf_diff modes are SFU/issue-bound: one vector, the
+            // registers go to the 32 independent quadrature chains instead)
+            constexpr int U = is_cdf(MODE) ? 1 : is_spatial(MODE) ? 2 : 4;
             const int v0 = e0 >> 2, v1 = e1 >> 2;
             const long vbase = base >> 2;
             for (int vb = v0; vb < v1; vb += 32 * U) {   // warp-uniform trip count (the cdf_diff modes are warp-cooperative)
@@ -364,10 +349,17 @@ __global__ void __launch_bounds__(kThreads, is_cdf(MODE) ? 2 : 4) bottleneck_fwd
                         q.z = quantize1(yy[k].z, quant_mode, nn[k].z);
                         q.w = quantize1(yy[k].w, quant_mode, nn[k].w);
                     }
-                    l.x = elem_nll<MODE>(q.x - m4.x, ok, tc, gc, ss[k].x, uu[k].x);
-                    l.y = elem_nll<MODE>(q.y - m4.y, ok, tc, gc, ss[k].y, uu[k].y);
-                    l.z = elem_nll<MODE>(q.z - m4.z, ok, tc, gc, ss[k].z, uu[k].z);
-                    l.w = elem_nll<MODE>(q.w - m4.w, ok, tc, gc, ss[k].w, uu[k].w);
+                    if (MODE == MODE_CDF_BCAST) {      // the lane's four elements share one warp-uniform panel loop
+                        const float xs[4] = {q.x - m4.x, q.y - m4.y, q.z - m4.z, q.w - m4.w};
+                        float r[4];
+                        uniform_cdf_nll<4>(xs, ok, tc, r);
+                        l = make_float4(r[0], r[1], r[2], r[3]);
+                    } else {
+                        l.x = elem_nll<MODE>(q.x - m4.x, ok, tc, gc, ss[k].x, uu[k].x);
+                        l.y = elem_nll<MODE>(q.y - m4.y, ok, tc, gc, ss[k].y, uu[k].y);
+                        l.z = elem_nll<MODE>(q.z - m4.z, ok, tc, gc, ss[k].z, uu[k].z);
+                        l.w = elem_nll<MODE>(q.w - m4.w, ok, tc, gc, ss[k].w, uu[k].w);
+                    }
                     if (ok) {
                         if (y_tilde != nullptr) stg_stream(reinterpret_cast<float4 *>(y_tilde) + gi, q);
                         if (nll != nullptr) stg_stream(reinterpret_cast<float4 *>(nll) + gi, l);

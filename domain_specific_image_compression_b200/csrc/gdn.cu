@@ -111,39 +111,37 @@ __device__ __forceinline__ Quad load_quad(const float *__restrict__ bias_p, cons
     return q;
 }
 
-// 5 CTAs per SM: ptxas fits the GDN instance in 48 registers without spills (53 unconstrained = 4 CTAs).  Resident CTAs are what
-// keep bytes in flight here: the NCHW kernel (36 registers, 6 CTAs) reaches 98 % of the HBM peak, the IGDN instance of this kernel
-// (48 registers, 5 CTAs) 95 %, the GDN instance at 4 CTAs 88 %.
-template <bool INVERSE>
+// One CTA per CONTIGUOUS chunk of iters * kUnroll * blockDim float4 (32 KB at 256 threads, iters = 2), like the NCHW kernel: the
+// hardware hands chunks to SMs as they free up, and concurrently running CTAs touch one moving window of DRAM pages.  Round 1 ran
+// this as a persistent grid-stride loop (CTAs stepping gridDim * 32 KB apart): 93 % of the HBM peak against the NCHW kernel's 98 %
+// on the same bytes (profiles/r02b_kernel_sweep_quick.json).  5 CTAs per SM: ptxas fits the GDN instance in 48 registers.
+template <bool INVERSE, int ITERS>
 __global__ void __launch_bounds__(kThreads, 5) gdn_fwd_nhwc_kernel(const float4 *__restrict__ x, const float *__restrict__ bias_p,
                                                                 const float *__restrict__ beta_param,
                                                                 const float *__restrict__ gamma_weight, unsigned n4, int c4,
                                                                 float4 *__restrict__ y) {
+    constexpr int iters = ITERS;
     const Quad q = load_quad(bias_p, beta_param, gamma_weight, (int)(threadIdx.x % c4) * 4);
-    // a CTA walks CONTIGUOUS super-chunks of 2*kUnroll*blockDim float4 (32 KB at 256 threads): same DRAM-page friendly
-    // access as the NCHW kernel (the first NHWC version strode 4 KB apart inside one iteration: 83 % vs 97 % of peak)
-    const unsigned chunk = blockDim.x * kUnroll * 2;
-    for (unsigned base = blockIdx.x * chunk; base < n4; base += gridDim.x * chunk) {
+    const unsigned step = blockDim.x * kUnroll;
+    unsigned v0 = blockIdx.x * (step * (unsigned)iters) + threadIdx.x;      // chunk base is a multiple of blockDim, hence of c4
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const unsigned v0 = base + half * blockDim.x * kUnroll + threadIdx.x;
-            float4 a[kUnroll];
+    for (int it = 0; it < iters; ++it, v0 += step) {
+        float4 a[kUnroll];
 #pragma unroll
-            for (int k = 0; k < kUnroll; ++k) {
-                unsigned v = v0 + k * blockDim.x;
-                if (v < n4) a[k] = ldg_stream(x + v);
-            }
+        for (int k = 0; k < kUnroll; ++k) {
+            unsigned v = v0 + k * blockDim.x;
+            if (v < n4) a[k] = ldg_stream(x + v);
+        }
 #pragma unroll
-            for (int k = 0; k < kUnroll; ++k) {
-                unsigned v = v0 + k * blockDim.x;
-                if (v < n4) {
-                    float4 o;
-                    o.x = gdn1<INVERSE>(a[k].x, q.a[0], q.b[0], q.g[0]);
-                    o.y = gdn1<INVERSE>(a[k].y, q.a[1], q.b[1], q.g[1]);
-                    o.z = gdn1<INVERSE>(a[k].z, q.a[2], q.b[2], q.g[2]);
-                    o.w = gdn1<INVERSE>(a[k].w, q.a[3], q.b[3], q.g[3]);
-                    stg_stream(y + v, o);
-                }
+        for (int k = 0; k < kUnroll; ++k) {
+            unsigned v = v0 + k * blockDim.x;
+            if (v < n4) {
+                float4 o;
+                o.x = gdn1<INVERSE>(a[k].x, q.a[0], q.b[0], q.g[0]);
+                o.y = gdn1<INVERSE>(a[k].y, q.a[1], q.b[1], q.g[1]);
+                o.z = gdn1<INVERSE>(a[k].z, q.a[2], q.b[2], q.g[2]);
+                o.w = gdn1<INVERSE>(a[k].w, q.a[3], q.b[3], q.g[3]);
+                stg_stream(y + v, o);
             }
         }
     }
@@ -251,13 +249,17 @@ __global__ void __launch_bounds__(kThreads) gdn_bwd_kernel(const float *__restri
     }
 }
 
-// NHWC backward: persistent CTAs, thread-private sums for its channel quad, one smem fold per CTA, partials [3][C][gridDim.x]
-constexpr int kBwdNhwcU = 3;   // float4 of x and of g in flight per thread and pass: 6 x 16 B at 4 CTAs/SM (64 registers, no spills)
+// NHWC backward: one CTA per contiguous chunk of iters * U * blockDim float4 of x (and of g), thread-private sums for the thread's
+// channel quad, one shared-memory fold per CTA, partials [3][C][gridDim.x] folded per channel by the finalize kernel.
+// Round 1 used 592 persistent CTAs with a statically dealt bulk and a finely dealt tail: 88-89 % of the HBM peak at the 256^2 site
+// where the NCHW kernel (one CTA per chunk, dynamic dispatch) reaches 99 % on the same bytes.  The price of the chunked grid is one
+// partial per (chunk, channel): 0.8 % extra traffic at 4096-float4 chunks.
+constexpr int kBwdNhwcU = 2;   // float4 of x and of g in flight per thread and pass
 
 template <bool INVERSE>
 __global__ void __launch_bounds__(kThreads, 4) gdn_bwd_nhwc_kernel(const float4 *__restrict__ x, const float *__restrict__ bias_p,
                                                                 const float4 *__restrict__ g, const float *__restrict__ beta_param,
-                                                                const float *__restrict__ gamma_weight, unsigned n4, int C,
+                                                                const float *__restrict__ gamma_weight, unsigned n4, int C, int iters,
                                                                 float4 *__restrict__ dx, float *__restrict__ part) {
     extern __shared__ float sm[];  // [blockDim.x][12]
     const int c4 = C >> 2;
@@ -265,9 +267,9 @@ __global__ void __launch_bounds__(kThreads, 4) gdn_bwd_nhwc_kernel(const float4 
     const Quad q = load_quad(bias_p, beta_param, gamma_weight, cq * 4);
     float ab[4] = {0.f, 0.f, 0.f, 0.f}, ag[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
     constexpr int U = kBwdNhwcU;
-    // one pass: U float4 of x and of g per thread in flight, blockDim apart (every stride is a multiple of blockDim, hence of C/4,
-    // so the thread keeps its channel quad)
-    auto pass = [&](unsigned v0) {
+    const unsigned step = blockDim.x * U;
+    unsigned v0 = blockIdx.x * (step * (unsigned)iters) + threadIdx.x;   // every stride is a multiple of blockDim, hence of C/4
+    for (int it = 0; it < iters; ++it, v0 += step) {
         float4 xa[U], ga[U];
 #pragma unroll
         for (int k = 0; k < U; ++k) {
@@ -287,19 +289,7 @@ __global__ void __launch_bounds__(kThreads, 4) gdn_bwd_nhwc_kernel(const float4 
                 stg_stream(dx + v, o);
             }
         }
-    };
-    // Bulk: whole rounds of contiguous super-chunks (4 passes = 48 KB of x per CTA and round at 256 threads), statically dealt.
-    // Tail: what is left after the last whole round is dealt out pass by pass (12 KB granules), so no CTA ends up with a whole
-    // extra super-chunk: at a 128^2 site (2731 super-chunks over 592 CTAs) a static deal alone would leave 5-vs-4.6 = 9 % idle.
-    const unsigned gran = blockDim.x * U;
-    const unsigned chunk = gran * 4;
-    const unsigned round = gridDim.x * chunk;
-    const unsigned full = (n4 / round) * round;
-    for (unsigned base = blockIdx.x * chunk; base < full; base += round) {
-#pragma unroll
-        for (int part_i = 0; part_i < 4; ++part_i) pass(base + part_i * gran + threadIdx.x);
     }
-    for (unsigned base = full + blockIdx.x * gran; base < n4; base += gridDim.x * gran) pass(base + threadIdx.x);
     float *mine = sm + threadIdx.x * 12;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { mine[j] = ab[j]; mine[4 + j] = ag[j]; mine[8 + j] = ax[j]; }
@@ -351,7 +341,17 @@ __global__ void __launch_bounds__(128) gdn_bwd_finalize_kernel(const float *__re
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int nhwc_threads(int C) { return (C / 4) * (kThreads / (C / 4)); }  // largest multiple of C/4 that is <= 256
-inline int nhwc_bwd_grid() { return sm_count() * 4; }
+// chunk sizing for the NHWC kernels: as many passes per CTA as keep at least ~8 CTAs per SM in the grid (small sites get one
+// pass per CTA so that every SM has work), at most `max_iters`
+inline int nhwc_iters(long n4, int per_pass, int max_iters) {
+    long it = n4 / ((long)per_pass * sm_count() * 8);
+    return (int)(it < 1 ? 1 : (it > max_iters ? max_iters : it));
+}
+inline int nhwc_bwd_iters(long n4, int threads) { return nhwc_iters(n4, threads * kBwdNhwcU, n4 > (64L << 20) ? 16 : 8); }
+inline long nhwc_bwd_grid(long n4, int threads) {
+    const long chunk = (long)threads * kBwdNhwcU * nhwc_bwd_iters(n4, threads);
+    return (n4 + chunk - 1) / chunk;
+}
 inline int bwd_chunks(int HW) {
     int per = kChunk4 * 4;
     return (HW + per - 1) / per;
@@ -359,8 +359,8 @@ inline int bwd_chunks(int HW) {
 
 SIC_REGISTER_KERNEL("gdn_fwd_vec_kernel<0>", gdn_fwd_vec_kernel<false>);
 SIC_REGISTER_KERNEL("gdn_fwd_vec_kernel<1>", gdn_fwd_vec_kernel<true>);
-SIC_REGISTER_KERNEL("gdn_fwd_nhwc_kernel<0>", gdn_fwd_nhwc_kernel<false>);
-SIC_REGISTER_KERNEL("gdn_fwd_nhwc_kernel<1>", gdn_fwd_nhwc_kernel<true>);
+SIC_REGISTER_KERNEL("gdn_fwd_nhwc_kernel<0,2>", gdn_fwd_nhwc_kernel<false, 2>);
+SIC_REGISTER_KERNEL("gdn_fwd_nhwc_kernel<1,2>", gdn_fwd_nhwc_kernel<true, 2>);
 SIC_REGISTER_KERNEL("gdn_bwd_kernel<0,1>", gdn_bwd_kernel<false, true>);
 SIC_REGISTER_KERNEL("gdn_bwd_kernel<1,1>", gdn_bwd_kernel<true, true>);
 SIC_REGISTER_KERNEL("gdn_bwd_nhwc_kernel<0>", gdn_bwd_nhwc_kernel<false>);
@@ -388,10 +388,13 @@ extern "C" int sic_gdn_fwd(const float *x, const float *bias, const float *beta_
     } else if (channels_last && C % 4 == 0 && C <= 4 * kThreads && al) {
         unsigned n4 = (unsigned)(n / 4);
         const int c4 = C / 4, threads = nhwc_threads(C);
-        long want = ((long)n4 + threads * kUnroll * 2 - 1) / (threads * kUnroll * 2);
-        unsigned grid = (unsigned)(want < (long)sms * 32 ? want : (long)sms * 32);
-        if (inverse) gdn_fwd_nhwc_kernel<true><<<grid, threads, 0, st>>>((const float4 *)x, bias, beta_param, gamma_weight, n4, c4, (float4 *)y);
-        else gdn_fwd_nhwc_kernel<false><<<grid, threads, 0, st>>>((const float4 *)x, bias, beta_param, gamma_weight, n4, c4, (float4 *)y);
+        const int iters = nhwc_iters(n4, threads * kUnroll, 2);
+        const long chunk = (long)threads * kUnroll * iters;
+        const unsigned grid = (unsigned)(((long)n4 + chunk - 1) / chunk);
+#define SIC_FWD_NHWC(INV, IT) gdn_fwd_nhwc_kernel<INV, IT><<<grid, threads, 0, st>>>((const float4 *)x, bias, beta_param, gamma_weight, n4, c4, (float4 *)y)
+        if (inverse) { if (iters == 2) SIC_FWD_NHWC(true, 2); else SIC_FWD_NHWC(true, 1); }
+        else { if (iters == 2) SIC_FWD_NHWC(false, 2); else SIC_FWD_NHWC(false, 1); }
+#undef SIC_FWD_NHWC
     } else {
         long want = (n + kThreads - 1) / kThreads;
         unsigned grid = (unsigned)(want < (long)sms * 16 ? want : (long)sms * 16);
@@ -405,7 +408,8 @@ extern "C" int sic_gdn_fwd(const float *x, const float *bias, const float *beta_
 extern "C" size_t sic_gdn_bwd_workspace_bytes(int B, int C, int HW) {
     if (B <= 0 || C <= 0 || HW <= 0) return 0;
     size_t nchw = (size_t)3 * C * B * bwd_chunks(HW) * sizeof(float);
-    size_t nhwc = (size_t)3 * C * nhwc_bwd_grid() * sizeof(float);
+    size_t nhwc = 0;
+    if (C % 4 == 0 && C <= 4 * kThreads) nhwc = (size_t)3 * C * nhwc_bwd_grid((long)B * C * HW / 4, nhwc_threads(C)) * sizeof(float);
     return nchw > nhwc ? nchw : nhwc;
 }
 
@@ -428,12 +432,11 @@ extern "C" int sic_gdn_bwd(const float *x, const float *bias, const float *g, co
         }
         const int threads = nhwc_threads(C);
         const unsigned n4 = (unsigned)(n / 4);
-        const long per_cta = (long)threads * kBwdNhwcU * 4;      // float4 per CTA iteration (the kernel's super-chunk)
-        long want = ((long)n4 + per_cta - 1) / per_cta;
-        const unsigned grid = (unsigned)(want < nhwc_bwd_grid() ? want : nhwc_bwd_grid());
+        const int iters = nhwc_bwd_iters(n4, threads);
+        const unsigned grid = (unsigned)nhwc_bwd_grid(n4, threads);
         const size_t smem = (size_t)threads * 12 * sizeof(float);
-        if (inverse) gdn_bwd_nhwc_kernel<true><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, (float4 *)dx, part);
-        else gdn_bwd_nhwc_kernel<false><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, (float4 *)dx, part);
+        if (inverse) gdn_bwd_nhwc_kernel<true><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, iters, (float4 *)dx, part);
+        else gdn_bwd_nhwc_kernel<false><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, iters, (float4 *)dx, part);
         SIC_CHECK_LAUNCH("sic_gdn_bwd (nhwc)");
         gdn_bwd_finalize_kernel<<<C, 128, 0, st>>>(part, beta_param, gamma_weight, C, (long)grid, dbeta_param, dgamma_weight, dbias);
         SIC_CHECK_LAUNCH("sic_gdn_bwd finalize");

@@ -333,6 +333,64 @@ def gdn_dense(x: torch.Tensor, beta_param: torch.Tensor, gamma_param: torch.Tens
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# N4: tail of the hyper-synthesis transform
+class _HyperTail(torch.autograd.Function):
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, t, w1s, b1s, w2s, b2s, w1n, b1n, w2n, b2n, min_nu: float, max_nu: float):
+        lib = _lib.load()
+        t, cl = _dense_layout(t, "t")
+        if t.dim() != 4:
+            raise _lib.SicError("hyper_tail expects the [B,N,h,w] output of h_s.h_s")
+        B, N, H, W = t.shape
+        M = w2s.shape[0]
+        ws = [_require_cuda_f32(w, "mlp parameter") for w in (w1s, b1s, w2s, b2s, w1n, b1n, w2n, b2n)]
+        want = [N * N, N, M * N, M] * 2
+        if [w.numel() for w in ws] != want or w2n.shape[0] != M:
+            raise _lib.SicError(f"hyper_tail: MLP parameters do not match N={N}, M={M}")
+        sigma = torch.empty((B, M, 1, 1), dtype=torch.float32, device=t.device)
+        nu = torch.empty((B, M, 1, 1), dtype=torch.float32, device=t.device)
+        need = any(ctx.needs_input_grad[:9])
+        save = torch.empty(lib.sic_hyper_tail_save_floats(B, N, M), dtype=torch.float32, device=t.device) if need else None
+        with torch.cuda.device(t.device):
+            _launch(lib.sic_hyper_tail_fwd(_ptr(t), B, N, M, H * W, cl, *[_ptr(w) for w in ws], float(min_nu), float(max_nu), _ptr(sigma),
+                                           _ptr(nu), _ptr(save), _stream()), "sic_hyper_tail_fwd")
+        if need:
+            ctx.save_for_backward(sigma, save, *ws)
+        ctx.cfg = (B, N, M, H, W, cl, float(min_nu), float(max_nu), t.shape, t.stride())
+        ctx.shapes = [w.shape for w in (w1s, b1s, w2s, b2s, w1n, b1n, w2n, b2n)]
+        ctx.set_materialize_grads(False)
+        return sigma, nu
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g_sigma, g_nu):
+        lib = _lib.load()
+        sigma, save, w1s, b1s, w2s, b2s, w1n, b1n, w2n, b2n = ctx.saved_tensors
+        B, N, M, H, W, cl, min_nu, max_nu, t_shape, t_stride = ctx.cfg
+        g_sigma = None if g_sigma is None else _require_cuda_f32(g_sigma, "g_sigma")
+        g_nu = None if g_nu is None else _require_cuda_f32(g_nu, "g_nu")
+        dev = sigma.device
+        dt = torch.empty_strided(t_shape, t_stride, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        grads = [torch.empty(shp, dtype=torch.float32, device=dev) for shp in ctx.shapes]
+        scratch = torch.empty(lib.sic_hyper_tail_scratch_floats(B, N, M), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sic_hyper_tail_bwd(_ptr(g_sigma), _ptr(g_nu), _ptr(sigma), _ptr(save), B, N, M, H * W, cl, _ptr(w1s), _ptr(w2s),
+                                              _ptr(w1n), _ptr(w2n), min_nu, max_nu, _ptr(dt), *[_ptr(g) for g in grads], _ptr(scratch),
+                                              _stream()), "sic_hyper_tail_bwd")
+        global launch_count
+        launch_count += 2
+        return (dt, *grads, None, None)
+
+
+def hyper_tail(t: torch.Tensor, mlp_sigma, mlp_nu, min_nu: float, max_nu: float):
+    """N4: pool -> mlp_sigma / mlp_nu -> exp / clamp in one launch (layers.py:141-152 + model.py:54-55).  `t`: output of h_s.h_s;
+    mlp_*: the reference's nn.Sequential(Conv2d(N,N,1), ReLU, Conv2d(N,M,1)).  Returns (sigma, nu) as [B,M,1,1] (K1's layout)."""
+    return _HyperTail.apply(t, mlp_sigma[0].weight, mlp_sigma[0].bias, mlp_sigma[2].weight, mlp_sigma[2].bias,
+                            mlp_nu[0].weight, mlp_nu[0].bias, mlp_nu[2].weight, mlp_nu[2].bias, float(min_nu), float(max_nu))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # N3: SSIM statistics of one MS-SSIM scale
 class _SSIMStats(torch.autograd.Function):
     @staticmethod

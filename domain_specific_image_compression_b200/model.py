@@ -22,6 +22,9 @@ from .layers import AnalysisTransform, HyperAnalysis, HyperSynthesis, SynthesisT
 from .losses import multi_scale_ssim
 
 
+FUSE_HYPER_TAIL = True      # False: run the hyper-synthesis tail as the reference's eager op chain (layers.py:141-152, model.py:54-55)
+
+
 class CompressionModel(nn.Module):
     def __init__(self, N=128, M=192, spatial_params=False, min_nu=1.1, max_nu=100.0, likelihood: str = "density"):
         super().__init__()
@@ -47,6 +50,13 @@ class CompressionModel(nn.Module):
 
     def _student_params(self, z_tilde, like):
         """model.py:47-55: hyper-synthesis + sigma/nu post-processing.  Returns kernel-layout and dict-layout tensors."""
+        if not self.spatial_params and FUSE_HYPER_TAIL:
+            # N4: pool -> two MLPs -> exp / clamp as ONE kernel with a fixed, batch-size-independent summation order (the eager
+            # chain is ~15 launches, and its cuDNN/cuBLAS GEMMs may round differently at different batch sizes, which would
+            # desynchronise encoder and decoder tables)
+            t = self.h_s.h_s(z_tilde)
+            sigma_k, nu_k = F_sic.hyper_tail(t, self.h_s.mlp_sigma, self.h_s.mlp_nu, self.min_nu, self.max_nu)
+            return sigma_k, nu_k, sigma_k.expand_as(like), nu_k.expand_as(like)
         log_sigma, log_nu = self.h_s(z_tilde)
         if self.spatial_params:
             sigma = torch.exp(log_sigma)

@@ -197,15 +197,18 @@ class FlatTrainer:
 class HostFedLoop:
     """Feeds a (captured or eager) step from pinned HOST batches without stalling the device on the copies.
 
-    Per step: the batch goes host -> device on a copy stream into one of two landing buffers while the previous step is still
+    Per step: the batch goes host -> device on its own copy stream into one of two landing buffers while the previous step is still
     computing; the step stream waits for that copy, moves the 12.6 MB batch into the step's static input (device-to-device),
-    runs the step; the scalar loss goes device -> host on the copy stream and is handed back ONE STEP LATE, so the host never
+    runs the step; the scalar loss goes device -> host on a second copy stream and is handed back ONE STEP LATE, so the host never
     blocks on the step it has just enqueued.  Every step still pays its own H2D and D2H; they are simply no longer serialised
     with the kernels (round 1: blocking copy_ before and after the replay, 0.14 ms/step on one GPU, 0.50 ms at eight)."""
 
     def __init__(self, run_step: Callable[[], torch.Tensor], x_static: torch.Tensor):
         self.run_step, self.x_static = run_step, x_static
-        self.copy_stream = torch.cuda.Stream(device=x_static.device)
+        # two copy streams: on ONE in-order stream the next batch's H2D would queue behind the previous loss's D2H, which waits
+        # for the previous step to finish - the H2D then ran between the steps instead of under them (measured: +0.21 ms/step)
+        self.h2d_stream = torch.cuda.Stream(device=x_static.device)
+        self.d2h_stream = torch.cuda.Stream(device=x_static.device)
         self.land = [torch.empty_like(x_static) for _ in range(2)]
         self.loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.h2d_done = [torch.cuda.Event() for _ in range(2)]
@@ -218,10 +221,10 @@ class HostFedLoop:
     def stage(self, x_host: torch.Tensor) -> None:
         """Start the host->device copy of the batch of the NEXT step() call."""
         k = self.i % 2
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.consumed[k])          # the step that last read this landing buffer has moved it on
+        with torch.cuda.stream(self.h2d_stream):
+            self.h2d_stream.wait_event(self.consumed[k])           # the step that last read this landing buffer has moved it on
             self.land[k].copy_(x_host, non_blocking=True)
-            self.h2d_done[k].record(self.copy_stream)
+            self.h2d_done[k].record(self.h2d_stream)
         self._staged = True
 
     def step(self, x_host_next: Optional[torch.Tensor] = None) -> Optional[float]:
@@ -237,10 +240,10 @@ class HostFedLoop:
         self.consumed[k].record(main)
         loss = self.run_step()
         self.step_done[k].record(main)
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.step_done[k])
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(self.step_done[k])
             self.loss_host[k].copy_(loss, non_blocking=True)
-            self.d2h_done[k].record(self.copy_stream)
+            self.d2h_done[k].record(self.d2h_stream)
         self.i += 1
         self._staged = False
         if x_host_next is not None:

@@ -145,6 +145,27 @@ int sic_gdn_dense_dgamma(const float *x, const float *h, long positions, int C, 
                          size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * N4  tail of the hyper-synthesis transform in one launch: layers.py:141-152 (AdaptiveAvgPool2d(1) -> mlp_sigma / mlp_nu, two 1x1
+ * convolutions with a ReLU each) + model.py:54-55 (exp, mean over an already constant map, clamp of nu); the decoder runs the same
+ * chain at eval_selfcontained_entropy.py:99-106 between the z decode and the y tables.
+ *   t [B, N, HW] (NCHW) or [B, HW, N] (channels_last != 0): output of h_s.h_s (the two transposed convolutions + ReLU, cuDNN).
+ *   w1* [N, N], b1* [N], w2* [M, N], b2* [M]: the 1x1-conv weights of mlp_sigma (s) / mlp_nu (n), as stored ([out, in, 1, 1]).
+ *   sigma, nu [B, M]: K1 / K3's broadcast layout; nu clamped to [min_nu, max_nu], sigma = exp(log_sigma) unclamped (model.py:54).
+ *   save (nullable; training): sic_hyper_tail_save_floats(B,N,M) floats kept for the backward (pooled input, hidden layers, exp(log_nu)).
+ * Fixed summation order, independent of the batch size: encoder and decoder derive bit-identical sigma / nu from identical z.
+ * bwd: dsigma / dnu [B, M] (nullable = 0) -> dt (layout of t, nullable) and the eight parameter gradients (summed over the batch in a
+ * fixed order); scratch: sic_hyper_tail_scratch_floats(B,N,M) floats.  Two launches. */
+size_t sic_hyper_tail_save_floats(int B, int N, int M);
+size_t sic_hyper_tail_scratch_floats(int B, int N, int M);
+int sic_hyper_tail_fwd(const float *t, int B, int N, int M, int HW, int channels_last, const float *w1s, const float *b1s,
+                       const float *w2s, const float *b2s, const float *w1n, const float *b1n, const float *w2n, const float *b2n,
+                       float min_nu, float max_nu, float *sigma, float *nu, float *save, void *stream);
+int sic_hyper_tail_bwd(const float *dsigma, const float *dnu, const float *sigma, const float *save, int B, int N, int M, int HW,
+                       int channels_last, const float *w1s, const float *w2s, const float *w1n, const float *w2n, float min_nu,
+                       float max_nu, float *dt, float *dw1s, float *db1s, float *dw2s, float *db2s, float *dw1n, float *db1n,
+                       float *dw2n, float *db2n, float *scratch, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * K4  symbols: eval_selfcontained_entropy.py:39-40,48 / :52-53,62 (per patch, no host sync).
  *   q [B,n_per_patch] float latent; do_round != 0 applies torch.round first.
  *   mins[b] = floor(min q_b) - tail ; maxs[b] = ceil(max q_b) + tail ; sym = int32(q) - mins[b]. */

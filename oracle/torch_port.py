@@ -79,6 +79,11 @@ def hyper_synthesis(sd, z, spatial_params=False):
     t = F.relu(_deconv(sd, "h_s.h_s.2", t))
     if spatial_params:
         return _conv(sd, "h_s.to_sigma", t, 1, 3), _conv(sd, "h_s.to_nu", t, 1, 3)
+    return hyper_heads(sd, t)
+
+
+def hyper_heads(sd, t):
+    """layers.py:146-151: pool -> mlp_sigma / mlp_nu -> expand over (h,w)."""
     pooled = F.adaptive_avg_pool2d(t, 1)
     heads = []
     for name in ("h_s.mlp_sigma", "h_s.mlp_nu"):
@@ -86,6 +91,15 @@ def hyper_synthesis(sd, z, spatial_params=False):
         u = F.conv2d(u, sd[name + ".2.weight"], sd[name + ".2.bias"])
         heads.append(u.expand(-1, -1, t.size(2), t.size(3)))
     return heads[0], heads[1]
+
+
+def hyper_tail(sd, t, min_nu=2.0, max_nu=100.0):
+    """What follows the two transposed convolutions of h_s when spatial_params=False: layers.py:146-151 then model.py:54-55.
+    Returns (sigma, nu) as [B,M,1,1]."""
+    log_sigma, log_nu = hyper_heads(sd, t)
+    sigma = torch.exp(log_sigma).mean(dim=(2, 3), keepdim=True)
+    nu = torch.clamp(torch.exp(log_nu).mean(dim=(2, 3), keepdim=True), min_nu, max_nu)
+    return sigma, nu
 
 
 def studentt_nll(x, sigma, nu):

@@ -4,9 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from domain_specific_image_compression_b200 import functional as F
 dev = torch.device("cuda", 0)
-which = sys.argv[1] if len(sys.argv) > 1 else "all"
+which = sys.argv[1] if len(sys.argv) > 1 else "all"      # one target, or several separated by commas
+which_set = set(which.split(","))
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-if which in ("all", "k1"):
+if which_set & {"all", "k1"}:
     y = torch.randn(16, 320, 128, 128, device=dev) * 3
     sg = torch.exp(torch.randn(16, 320, 1, 1, device=dev)); nu = torch.exp(torch.randn(16, 320, 1, 1, device=dev) + 1.5)
     for _ in range(reps):
@@ -20,7 +21,7 @@ if which in ("all", "k1"):
         for _ in range(reps):
             F.bottleneck(y, sg, nu, quant="noise", lik="cdf_diff")
     del y, yr, yt, nll
-if which in ("all", "gdn"):
+if which_set & {"all", "gdn"}:
     for fmt in (torch.contiguous_format, torch.channels_last):
         x = torch.randn(16, 128, 256, 256, device=dev).contiguous(memory_format=fmt)
         g = torch.randn(16, 128, 256, 256, device=dev).contiguous(memory_format=fmt)
@@ -31,24 +32,24 @@ if which in ("all", "gdn"):
             yv = F.gdn(xr, beta, w, False)
             torch.autograd.grad(yv, (xr, beta, w), g)
         del x, g, xr, yv
-if which in ("all", "dense"):
+if which_set & {"all", "dense"}:
     x = torch.randn(16, 128, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
     beta = torch.sqrt(torch.rand(128, device=dev) + 0.5)
     gm = torch.sqrt(torch.rand(128, 128, device=dev) * 0.02 + torch.eye(128, device=dev) * 0.1 + 2.0 ** -18)
     for _ in range(reps):
         F.gdn_dense(x, beta, gm, False)
-if which in ("dense192",):
+if which_set & {"dense192"}:
     x = torch.randn(8, 192, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
     beta = torch.sqrt(torch.rand(192, device=dev) + 0.5)
     gm = torch.sqrt(torch.rand(192, 192, device=dev) * 0.02 + torch.eye(192, device=dev) * 0.1 + 2.0 ** -18)
     for _ in range(reps):
         F.gdn_dense(x, beta, gm, False)
-if which in ("cdf",):
+if which_set & {"cdf"}:
     y = torch.randn(16, 320, 128, 128, device=dev) * 3
     sg = torch.exp(torch.randn(16, 320, 1, 1, device=dev)); nu = torch.exp(torch.randn(16, 320, 1, 1, device=dev) + 1.5)
     for _ in range(reps):
         F.bottleneck(y, sg, nu, quant="noise", lik="cdf_diff")
-if which in ("dense_bwd",):
+if which_set & {"dense_bwd"}:
     for C, B in ((128, 16), (192, 8)):
         x = torch.randn(B, C, 256, 256, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
         beta = torch.sqrt(torch.rand(C, device=dev) + 0.5).requires_grad_(True)
@@ -57,7 +58,7 @@ if which in ("dense_bwd",):
             yv = F.gdn_dense(x, beta, gm, False)
             torch.autograd.grad(yv, (x, beta, gm), torch.randn_like(yv))
         del x, yv
-if which in ("codec",):
+if which_set & {"codec"}:
     import domain_specific_image_compression_b200 as sic
     torch.manual_seed(0)
     m = sic.CompressionModel(N=128, M=192, min_nu=2.0).to(dev).eval()
@@ -67,7 +68,7 @@ if which in ("codec",):
     for _ in range(reps):
         comp = m.compress(xi)
         m.decompress(comp)
-if which in ("ssim",):
+if which_set & {"ssim"}:
     from domain_specific_image_compression_b200 import losses
     a = torch.rand(16, 3, 256, 256, device=dev, requires_grad=True); b = torch.rand(16, 3, 256, 256, device=dev)
     for _ in range(reps):

@@ -256,8 +256,11 @@ def test_dense_gdn_backward_and_module():
     bd, gd = m.beta.detach().double().requires_grad_(True), m.gamma.detach().double().requires_grad_(True)
     s = torch.nn.functional.conv2d(xd * xd, (gd * gd - 2.0 ** -18).view(64, 64, 1, 1), bd * bd - 2.0 ** -18)
     ((xd / torch.sqrt(s)) * go.double()).sum().backward()
+    # against the UNtruncated gamma: the tensor-core passes consume gamma at TF32 (10 mantissa bits), the documented tolerance-only
+    # mode of the dense path (same 1e-3 bar as the forward, test_dense_gdn_forward_vs_oracle); the tight comparison, against the
+    # oracle with gamma at TF32, is test_dense_gdn_fused_backward_vs_float64
     for mine, ref in ((x.grad, xd.grad), (m.beta.grad, bd.grad), (m.gamma.grad, gd.grad)):
-        assert float((mine.double() - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-7
+        assert float((mine.double() - ref).abs().max()) <= 1e-3 * float(ref.abs().max()) + 1e-7
     assert m.gamma_conv.weight.grad is None                       # the diagonal conv is the unused one in dense mode
     with pytest.raises(sic.SicError):
         F = _F()
@@ -326,12 +329,12 @@ def test_dense_gdn_fused_backward_vs_float64(shape, inverse):
 
 @pytest.mark.parametrize("inverse", [False, True])
 def test_channels_last_backward_full_rounds_and_tail_vs_nchw(inverse):
-    """A site large enough (8.4M elements) that the persistent channels_last backward kernel runs whole rounds of super-chunks
-    AND the finely dealt remainder: its dx must equal the NCHW kernel's (same per-element arithmetic), its parameter and
-    bias gradients the NCHW kernel's up to summation order."""
+    """A site large enough (8.4M elements) that the channels_last backward kernel runs several passes per chunk and hundreds of
+    chunks (one partial per chunk and channel): its dx must equal the NCHW kernel's (same per-element arithmetic), its
+    parameter and bias gradients the NCHW kernel's up to summation order."""
     F = _F()
     g = torch.Generator(device="cuda").manual_seed(17 + inverse)
-    shape = (4, 128, 128, 128)
+    shape = (4, 128, 128, 127)                      # 127: the last chunk is ragged
     x0 = torch.randn(shape, device="cuda", generator=g) * 2
     go = torch.randn(shape, device="cuda", generator=g)
     b0 = torch.sqrt(torch.rand(128, device="cuda", generator=g) + 0.5)

@@ -61,8 +61,21 @@ def test_forward_matches_eager_port_on_same_gpu(golden):
         m.eval()
         out = m(x, "round")
         ref = TP.forward(sd, x, "round", training=False)
-        for k in ("y", "z", "y_tilde", "z_tilde", "sigma", "nu", "x_hat"):
+        for k in ("y", "z", "y_tilde", "z_tilde", "x_hat"):
             assert torch.equal(out[k], ref[k]), k
+        # P1 / N4: sigma, nu come from the fused hyper-synthesis tail (fixed summation order; a library GEMM cannot be matched bit for
+        # bit), so they agree to accumulation-order error; with the tail switched back to the eager chain they are bit-equal
+        for k in ("sigma", "nu"):
+            assert out[k].shape == ref[k].shape and out[k].stride() == ref[k].stride()
+            assert float(((out[k] - ref[k]).abs() / ref[k].abs()).max()) <= 5e-6, k
+        from domain_specific_image_compression_b200 import model as M_
+        M_.FUSE_HYPER_TAIL = False
+        try:
+            out_e = m(x, "round")
+        finally:
+            M_.FUSE_HYPER_TAIL = True
+        for k in ("sigma", "nu", "y_tilde", "x_hat"):
+            assert torch.equal(out_e[k], ref[k]), k
         for k in ("nll_y", "nll_z"):
             err = (out[k].double() - ref[k].double()).abs()
             assert bool((err <= 1e-4 + 1e-5 * ref[k].double().abs()).all()), k
