@@ -92,11 +92,25 @@ __device__ __forceinline__ float t_nll(float x, const TConst &c) {
 __device__ __constant__ float kGLx[4] = {0.1834346424956498f, 0.5255324099163290f, 0.7966664774136267f, 0.9602898564975363f};
 __device__ __constant__ float kGLw[4] = {0.3626837833783620f, 0.3137066458778873f, 0.2223810344533745f, 0.1012285362903763f};
 
+// One MUFU instruction each.  __log2f / exp2f wrap the same MUFU.LG2 / MUFU.EX2 in denormal handling (FSETP + FMUL before, FMUL /
+// FADD after: the r02c SASS count has 83 M FSETP next to 88 M MUFU); the quadrature's log argument is >= 1 and a density that
+// underflows to a denormal relative to the bin's peak contributes nothing, so the flush-to-zero forms are exact enough here.
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // scaled density: 2^(-B2 log2(1+t^2/nu) - eref)
 __device__ __forceinline__ float t_fs(float t, float inv_nu, float B2, float eref, float &l2, float &w) {
     w = fmaf(t * t, inv_nu, 1.0f);
-    l2 = __log2f(w);
-    return exp2f(fmaf(-B2, l2, -eref));
+    l2 = lg2_ftz(w);
+    return ex2_ftz(fmaf(-B2, l2, -eref));
 }
 
 // integral over [a,b], 0 <= a <= b, of the scaled density (S) and, if WANT_G, of density * dlog f/dnu (Q)
@@ -280,7 +294,7 @@ __device__ __forceinline__ bool retire_and_check_last(unsigned int *ticket) {
 // QUANT and HAS_MU are compile-time so that the prefetch registers of unused optional inputs (noise tensor, mu map)
 // disappear: the common training instance (broadcast, Philox, no mu) must stay <= 64 registers for 4 CTAs per SM.
 template <int MODE, bool VEC, int QUANT, bool HAS_MU>
-__global__ void __launch_bounds__(kThreads, is_cdf(MODE) ? 3 : 4) bottleneck_fwd_kernel(
+__global__ void __launch_bounds__(kThreads, MODE == MODE_CDF_SPATIAL ? 3 : 4) bottleneck_fwd_kernel(
     const float *__restrict__ y, const float *__restrict__ noise, uint64_t *__restrict__ philox,
     const float *__restrict__ mu_in, const float *__restrict__ sigma, const float *__restrict__ nu, Shape sh,
     int mu_layout, float *__restrict__ y_tilde, float *__restrict__ nll, float *__restrict__ bits, float *__restrict__ psum,

@@ -311,31 +311,50 @@ __global__ void __launch_bounds__(kThreads, 4) gdn_bwd_nhwc_kernel(const float4 
     }
 }
 
-// one CTA per channel: fixed-order float64 fold + chain rule through the squared re-parameterisation (layers.py:20-21)
-__global__ void __launch_bounds__(128) gdn_bwd_finalize_kernel(const float *__restrict__ part, const float *__restrict__ beta_param,
-                                                               const float *__restrict__ gamma_weight, int C, long P,
-                                                               float *__restrict__ dbeta_param, float *__restrict__ dgamma_weight,
-                                                               float *__restrict__ dbias) {
+// one CTA per channel: fixed-order float64 fold + chain rule through the squared re-parameterisation (layers.py:20-21).
+// The chunked NHWC backward leaves thousands of partials per channel (8192 at the 256^2 site); with 128 threads and one dependent
+// load per iteration the fold alone took ~35 us (r02c: 246 us of main kernel became 281 us per site).  512 threads, four independent
+// loads in flight per thread and array: the fold is back to a few microseconds.  Summation order is fixed by (thread, position).
+constexpr int kFinThreads = 512;
+__global__ void __launch_bounds__(kFinThreads) gdn_bwd_finalize_kernel(const float *__restrict__ part, const float *__restrict__ beta_param,
+                                                                     const float *__restrict__ gamma_weight, int C, long P,
+                                                                     float *__restrict__ dbeta_param, float *__restrict__ dgamma_weight,
+                                                                     float *__restrict__ dbias) {
     const int c = blockIdx.x;
+    const float *pb = part + (long)c * P, *pg = part + (long)C * P + (long)c * P, *px = part + 2 * (long)C * P + (long)c * P;
     double sb = 0.0, sg = 0.0, sx = 0.0;
-    for (long i = threadIdx.x; i < P; i += 128) {
-        sb += (double)part[(long)c * P + i];
-        sg += (double)part[(long)C * P + (long)c * P + i];
-        sx += (double)part[2 * (long)C * P + (long)c * P + i];
+    long i = threadIdx.x;
+    for (; i + 3 * kFinThreads < P; i += 4 * kFinThreads) {
+        float b0 = __ldcs(pb + i), b1 = __ldcs(pb + i + kFinThreads), b2 = __ldcs(pb + i + 2 * kFinThreads), b3 = __ldcs(pb + i + 3 * kFinThreads);
+        float g0 = __ldcs(pg + i), g1 = __ldcs(pg + i + kFinThreads), g2 = __ldcs(pg + i + 2 * kFinThreads), g3 = __ldcs(pg + i + 3 * kFinThreads);
+        float x0 = __ldcs(px + i), x1 = __ldcs(px + i + kFinThreads), x2 = __ldcs(px + i + 2 * kFinThreads), x3 = __ldcs(px + i + 3 * kFinThreads);
+        sb += ((double)b0 + (double)b1) + ((double)b2 + (double)b3);
+        sg += ((double)g0 + (double)g1) + ((double)g2 + (double)g3);
+        sx += ((double)x0 + (double)x1) + ((double)x2 + (double)x3);
     }
-    __shared__ double shb[4], shg[4], shx[4];
+    for (; i < P; i += kFinThreads) {
+        sb += (double)__ldcs(pb + i);
+        sg += (double)__ldcs(pg + i);
+        sx += (double)__ldcs(px + i);
+    }
+    __shared__ double shb[kFinThreads / 32], shg[kFinThreads / 32], shx[kFinThreads / 32];
     sb = warp_sum(sb);
     sg = warp_sum(sg);
     sx = warp_sum(sx);
     if ((threadIdx.x & 31) == 0) { shb[threadIdx.x >> 5] = sb; shg[threadIdx.x >> 5] = sg; shx[threadIdx.x >> 5] = sx; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        sb = (shb[0] + shb[1]) + (shb[2] + shb[3]);
-        sg = (shg[0] + shg[1]) + (shg[2] + shg[3]);
-        sx = (shx[0] + shx[1]) + (shx[2] + shx[3]);
-        if (dbeta_param) dbeta_param[c] = (float)(sb * 2.0 * (double)beta_param[c]);
-        if (dgamma_weight) dgamma_weight[c] = (float)(sg * 2.0 * (double)gamma_weight[c]);
-        if (dbias) dbias[c] = (float)sx;
+    if (threadIdx.x < 32) {
+        sb = threadIdx.x < kFinThreads / 32 ? shb[threadIdx.x] : 0.0;
+        sg = threadIdx.x < kFinThreads / 32 ? shg[threadIdx.x] : 0.0;
+        sx = threadIdx.x < kFinThreads / 32 ? shx[threadIdx.x] : 0.0;
+        sb = warp_sum(sb);
+        sg = warp_sum(sg);
+        sx = warp_sum(sx);
+        if (threadIdx.x == 0) {
+            if (dbeta_param) dbeta_param[c] = (float)(sb * 2.0 * (double)beta_param[c]);
+            if (dgamma_weight) dgamma_weight[c] = (float)(sg * 2.0 * (double)gamma_weight[c]);
+            if (dbias) dbias[c] = (float)sx;
+        }
     }
 }
 
@@ -438,7 +457,7 @@ extern "C" int sic_gdn_bwd(const float *x, const float *bias, const float *g, co
         if (inverse) gdn_bwd_nhwc_kernel<true><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, iters, (float4 *)dx, part);
         else gdn_bwd_nhwc_kernel<false><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, iters, (float4 *)dx, part);
         SIC_CHECK_LAUNCH("sic_gdn_bwd (nhwc)");
-        gdn_bwd_finalize_kernel<<<C, 128, 0, st>>>(part, beta_param, gamma_weight, C, (long)grid, dbeta_param, dgamma_weight, dbias);
+        gdn_bwd_finalize_kernel<<<C, kFinThreads, 0, st>>>(part, beta_param, gamma_weight, C, (long)grid, dbeta_param, dgamma_weight, dbias);
         SIC_CHECK_LAUNCH("sic_gdn_bwd finalize");
         return 0;
     }
@@ -454,7 +473,7 @@ extern "C" int sic_gdn_bwd(const float *x, const float *bias, const float *g, co
         else gdn_bwd_kernel<false, false><<<(unsigned)units, kThreads, 0, st>>>(x, bias, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
     }
     SIC_CHECK_LAUNCH("sic_gdn_bwd");
-    gdn_bwd_finalize_kernel<<<C, 128, 0, st>>>(part, beta_param, gamma_weight, C, (long)B * chunks, dbeta_param, dgamma_weight, dbias);
+    gdn_bwd_finalize_kernel<<<C, kFinThreads, 0, st>>>(part, beta_param, gamma_weight, C, (long)B * chunks, dbeta_param, dgamma_weight, dbias);
     SIC_CHECK_LAUNCH("sic_gdn_bwd finalize");
     return 0;
 }

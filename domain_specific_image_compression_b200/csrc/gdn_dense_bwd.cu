@@ -272,14 +272,28 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
                 xn[k] = (r < vld) ? ldg_keep(src + (long)r * V + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        // DRAM latency is taken by an L2 prefetch two tiles ahead (one thread, one bulk instruction, no registers); the register
-        // loads one sub-step ahead then hit L2, so the in-flight window is not bounded by the producers' register file
+        // DRAM latency of the producers' tensor is taken by an L2 prefetch two tiles ahead (one thread, one bulk instruction, no
+        // registers); the register loads one sub-step ahead then hit L2.  The tensors only the EPILOGUE reads (g in pass 1; x and
+        // direct in pass 2) are prefetched for the tile the producers are just starting: the epilogue of that tile runs one tile
+        // time (~3 us) later.  Round 2's first capture prefetched them two tiles ahead as well: 57-85 MB of lines in flight across
+        // 148 CTAs, L2 read hit rate 29 % / 19 % and twice the algorithmic DRAM reads (profiles/r02c_ncu_dense_bwd.txt) - the lines
+        // were evicted before use.  SIC_DENSE_BWD_PF=far restores that behaviour for A/B timing.
         auto prefetch = [&](long t) {
             const long q0 = t * TN;
             if (use_prefetch && ptid == 0 && q0 < P) {
                 const long rows = (P - q0 < TN) ? (P - q0) : TN;
                 prefetch_l2_bulk(in0 + q0 * C, (uint32_t)(rows * C * 4));
-                if constexpr (!T::kFwd) prefetch_l2_bulk(in1 + q0 * C, (uint32_t)(rows * C * 4));    // g (pass 1) / x (pass 2) for the epilogue
+                if (use_prefetch == 2) {
+                    if constexpr (!T::kFwd) prefetch_l2_bulk(in1 + q0 * C, (uint32_t)(rows * C * 4));
+                    if constexpr (T::kBwd2) prefetch_l2_bulk(in2 + q0 * C, (uint32_t)(rows * C * 4));
+                }
+            }
+        };
+        auto prefetch_epilogue = [&](long t) {
+            const long q0 = t * TN;
+            if (use_prefetch == 1 && ptid == 0 && q0 < P) {
+                const long rows = (P - q0 < TN) ? (P - q0) : TN;
+                if constexpr (!T::kFwd) prefetch_l2_bulk(in1 + q0 * C, (uint32_t)(rows * C * 4));    // g (pass 1) / x (pass 2)
                 if constexpr (T::kBwd2) prefetch_l2_bulk(in2 + q0 * C, (uint32_t)(rows * C * 4));   // direct
             }
         };
@@ -287,6 +301,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
         prefetch(blockIdx.x + (long)gridDim.x);
         uint32_t u = 0;                              // sub-step counter: stage = u % NS, phase = (u / NS) & 1
         for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            prefetch_epilogue(tile);
 #pragma unroll 1
             for (int h = 0; h < KS; ++h, ++u) {
                 const uint32_t s = u % NS, ph = (u / NS) & 1;
@@ -365,6 +380,16 @@ __global__ void __launch_bounds__(kThreadsWS, 1) gdn_dense_ws_kernel(const float
     }
 }
 
+// 0: no L2 prefetch, 1 (default): epilogue-only tensors prefetched for the current tile, 2 (SIC_DENSE_BWD_PF=far): everything two ahead
+inline int dense_bwd_prefetch_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SIC_DENSE_BWD_PF");
+        v = !dense_prefetch_enabled() ? 0 : (e && e[0] == 'f') ? 2 : 1;
+    }
+    return v;
+}
+
 template <int C, int OP>
 int launch_dense_op(const char *what, const float *in0, const float *beta_param, const float *gamma_param, long P, float *out0,
                     const float *in1, const float *in2, float *out1, float *part, cudaStream_t st) {
@@ -375,7 +400,7 @@ int launch_dense_op(const char *what, const float *in0, const float *beta_param,
         set_error("%s: cannot reserve %zu B of shared memory: %s", what, smem, cudaGetErrorString(e));
         return (int)e;
     }
-    kern<<<dense_grid(P, WsCfg<C>::TN), kThreadsWS, smem, st>>>(in0, beta_param, gamma_param, P, dense_prefetch_enabled(),
+    kern<<<dense_grid(P, WsCfg<C>::TN), kThreadsWS, smem, st>>>(in0, beta_param, gamma_param, P, dense_bwd_prefetch_mode(),
                                                              dense_gamma_in_tmem(), out0, in1, in2, out1, part);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) {

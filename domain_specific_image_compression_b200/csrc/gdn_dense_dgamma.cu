@@ -7,9 +7,12 @@
 //
 //   producers (8 warps)  h tile and x tile, TN positions x C channels each, straight from channels-last memory -> h split EXACTLY
 //                        into tf32 hi + lo, x^2 likewise -> four shared-memory tiles in the NATURAL layout [position row][32-channel
-//                        128-byte chunk], SWIZZLE_128B.  No transpose anywhere: with K = positions that natural layout IS the
-//                        canonical MN-major UMMA operand layout (8 K-rows x 128 B of M/N per swizzle atom, atoms LBO apart along
-//                        M/N, 8-row groups SBO = 1024 B apart along K), for A = h^T and for B = (x^2)^T alike.
+//                        128-byte chunk].  No transpose anywhere: with K = positions that natural layout IS the canonical MN-major
+//                        UMMA operand layout, for A = h^T and for B = (x^2)^T alike.  For 32-bit (tf32) MN-major operands the only
+//                        layout the tensor core accepts is SWIZZLE_128B_BASE32B (cute: Layout_MN_SW128_32B_Atom, "for mn-major
+//                        tf32 operands, SW128_32B is the only available smem layout"): atoms of 4 K-rows x 128 B, the 32-byte chunk
+//                        index XORed with (row & 3), atoms LBO apart along M/N and SBO = 512 B apart along K.  (The first version
+//                        used the 16-byte SWIZZLE_128B pattern of the K-major kernels: the MMAs ran and returned zeros.)
 //   MMA warp             D[i, j] (TMEM, fp32, ONE accumulator that lives for the whole kernel) += hh*qh + hl*qh + hh*ql over K = 8
 //                        positions per instruction (a_major = b_major = MN in the instruction descriptor); the dropped hl*ql term is
 //                        2^-22 relative.  A plain tf32 product (truncating both operands) is biased by ~ -7e-4 relative, which
@@ -47,15 +50,21 @@ struct DgCfg {
     static_assert((kDgTN * (C / 4)) % kDgProdThreads == 0 && NS >= 2, "stage geometry");
 };
 
-// MN-major SWIZZLE_128B operand: 8 K-rows of 128 bytes per atom; atoms `lbo` bytes apart along M/N; 8-row groups 1024 B apart along K
+// MN-major SWIZZLE_128B_BASE32B operand (layout type 1): 4 K-rows of 128 bytes per atom; atoms `lbo` bytes apart along M/N;
+// 4-row groups 512 B apart along K
 __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)(lbo >> 4) << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;
     return d;
+}
+// byte offset of the 16-byte chunk c (0..7) of row r in 32-channel column block kb of a [rows x C] tile: Swizzle<2,5,2> on the byte
+// address, i.e. the 32-byte chunk index (c >> 1) XOR (r & 3)
+__device__ __forceinline__ uint32_t sw128b32_offset(int r, int kb, int c, int rows) {
+    return (uint32_t)kb * (uint32_t)rows * 128u + (uint32_t)r * 128u + (uint32_t)((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4));
 }
 __device__ __forceinline__ uint32_t idesc_tf32_mn(int M, int N) { return idesc_tf32(M, N) | (1u << 15) | (1u << 16); }
 
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) gdn_dense_dgamma_kernel(const f
 #pragma unroll
             for (int k = 0; k < PER; ++k) {
                 const int idx = tid + k * kDgProdThreads, r = idx / V, c4 = idx - r * V;
-                const uint32_t off = sw128_offset(r, c4 >> 3, c4 & 7, TN);
+                const uint32_t off = sw128b32_offset(r, c4 >> 3, c4 & 7, TN);
                 float4 hi, lo;
                 split_tf32(hn[k], hi, lo);
                 sts128(sHH + off, hi);
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) gdn_dense_dgamma_kernel(const f
                 for (int term = 0; term < 3; ++term) {                   // hh*qh, hl*qh, hh*ql
                     const uint32_t sa = term == 1 ? sHL : sHH, sb = term == 2 ? sQL : sQH;
 #pragma unroll
-                    for (int ks = 0; ks < TN / 8; ++ks) {                // 8 positions (one 1024-byte row group) per instruction
+                    for (int ks = 0; ks < TN / 8; ++ks) {                // 8 positions (two 4-row atoms, 1024 bytes) per instruction
                         const uint64_t dA = smem_desc_mn(sa + ks * 1024, LBO), dB = smem_desc_mn(sb + ks * 1024, LBO);
                         const uint32_t accumulate = (u | (uint32_t)term | (uint32_t)ks) != 0;
                         mma_tf32(tmem_base, dA, dB, idescA, accumulate);

@@ -22,8 +22,11 @@ for row in csv.reader(io.StringIO(src)):
     if not row:
         continue
     if row[0] == "Kernel Name":
-        cur = {"name": row[1], "cols": None, "ops": {}}
-        kernels.append(cur)
+        if kernels and kernels[-1]["name"] == row[1] and not kernels[-1].get("dup"):
+            cur = {"name": row[1], "cols": None, "ops": {}, "dup": True}     # the page prints most kernels twice (two views, same SASS)
+        else:
+            cur = {"name": row[1], "cols": None, "ops": {}}
+            kernels.append(cur)
     elif row[0] == "Address":
         cur["cols"] = {h: i for i, h in enumerate(row)}
     elif cur is not None and cur["cols"] is not None and row[0].startswith("0x"):
