@@ -63,6 +63,8 @@ def parse():
                     "internal NCHW<->NHWC transposes; GDN kernels run natively in either layout)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="cuDNN autotune is on by default (warm-up steps absorb it)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph")
+    ap.add_argument("--no-fuse-first-layer", action="store_true", help="keep g_a's first layer as cuDNN conv + GDN kernel (default: the fused "
+                    "conv 3->N 3x3 + bias + GDN tcgen05 kernel, forward and backward: layers.FUSE_FIRST_LAYER)")
     ap.add_argument("--pad-rgb", type=int, default=0, choices=[0, 4, 8], help="zero-pad the image-side channel axis of the first conv / "
                     "last transposed conv to 4 or 8 so cuDNN can use tensor-core kernels there (layers.PAD_RGB_CHANNELS; identity "
                     "in exact arithmetic, off by default)")
@@ -253,9 +255,10 @@ def run_ours(args):
                 mod.dense = True
     model.train()
     fmt = torch.contiguous_format if args.nchw else torch.channels_last
+    from domain_specific_image_compression_b200 import layers as _layers
     if args.pad_rgb:
-        from domain_specific_image_compression_b200 import layers as _layers
         _layers.PAD_RGB_CHANNELS = args.pad_rgb
+    _layers.FUSE_FIRST_LAYER = not (args.no_fuse_first_layer or args.pad_rgb or args.gdn == "dense" or args.nchw)
     model = model.to(memory_format=fmt)
     trainer = FlatTrainer(model, lr=1e-4, betas=(0.9, 0.999), grad_clip=1.0, bucket_bytes=int(args.bucket_mb * (1 << 20)))
     x_dev = synthetic_batch(B, H, W, 42 + rank, dev).contiguous(memory_format=fmt)
@@ -372,7 +375,7 @@ def run_ours(args):
                        "l2": "per-step working set (>= 5 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "conv_math": "cuDNN fp32 with TF32 allowed (PyTorch default, as the reference)",
                        "activation_layout": "NCHW" if args.nchw else "channels_last", "launch": graph_note,
-                       "rgb_channel_padding": args.pad_rgb, "gdn": args.gdn,
+                       "rgb_channel_padding": args.pad_rgb, "gdn": args.gdn, "fused_first_layer": bool(_layers.FUSE_FIRST_LAYER),
                        "gradient_buckets": [hi - lo for lo, hi, _, _ in trainer.buckets] if world > 1 else None,
                        "cudnn_benchmark": not args.no_cudnn_benchmark},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
@@ -408,12 +411,40 @@ def kernel_rooflines(cfg, dev, channels_last=True):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def time_it(fn, reps=10):
+    def time_it(fn, reps=10, big=False):
+        """big=True: the kernel streams >= 256 MB, twice the 126 MB L2 and walked front to back, so consecutive launches cannot
+        reuse each other's lines and no flush is needed (B200_PROFILING.md: "either flush L2 or use inputs larger than L2").
+        Flushing by WRITING 256 MB, as the small cases do, leaves the L2 full of dirty lines whose write-back (126 MB, ~8 % of a
+        1.6 GB kernel) is then billed to the kernel under test: ncu, which invalidates instead, timed the same launches 7 % faster.
+        The `reps` launches are captured into ONE CUDA graph and the replay is timed with events on the replaying stream: the
+        launch-to-launch gap is then the one the kernel sees inside the step (which is itself replayed as a graph) instead of
+        Python's dispatch time.  Median of 5 replays / reps."""
         for _ in range(3):
             fn()
+        if big:
+            try:
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    for _ in range(reps):
+                        fn()
+                ts = []
+                gr.replay()
+                for _ in range(5):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); gr.replay(); e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1) / reps)
+                del gr
+                ts.sort()
+                return ts[len(ts) // 2] * 1e-3
+            except Exception as e:                               # capture refused (allocator state, library call): eager timing below
+                print(f"[bench] kernel timing: graph capture failed ({type(e).__name__}: {str(e)[:120]}), timing eager launches", file=sys.stderr)
+                torch.cuda.synchronize()
         ts = []
         for _ in range(reps):
-            flush.zero_()
+            if not big:
+                flush.zero_()
             # a queued spin (~0.2 ms) lets the host run ahead: without it the GPU idles between e0 and the kernel while Python
             # (autograd dispatch, ~45 us for a backward) is still launching, and that idle time was being billed to the kernel
             torch.cuda._sleep(400_000)
@@ -431,19 +462,19 @@ def kernel_rooflines(cfg, dev, channels_last=True):
     beta = torch.sqrt(torch.rand(N, device=dev) + 0.5).requires_grad_(True)
     w = torch.sqrt(torch.rand(N, 1, 1, 1, device=dev) * 0.3 + 0.01).requires_grad_(True)
     n = x.numel()
-    t = time_it(lambda: F.gdn(x, beta, w, False))
+    t = time_it(lambda: F.gdn(x, beta, w, False), big=True)
     out["gdn_fwd"] = {"shape": list(x.shape), "bytes": 8 * n, "ms": t * 1e3, "gbs": 8 * n / t / 1e9}
     xr = x.clone().requires_grad_(True)
     y = F.gdn(xr, beta, w, False)
-    t = time_it(lambda: torch.autograd.grad(y, (xr, beta, w), g, retain_graph=True))
+    t = time_it(lambda: torch.autograd.grad(y, (xr, beta, w), g, retain_graph=True), big=True)
     out["gdn_bwd"] = {"shape": list(x.shape), "bytes": 12 * n, "ms": t * 1e3, "gbs": 12 * n / t / 1e9}
     xc = x.contiguous(memory_format=torch.channels_last)
     gc = g.contiguous(memory_format=torch.channels_last)
-    t = time_it(lambda: F.gdn(xc, beta, w, False))
+    t = time_it(lambda: F.gdn(xc, beta, w, False), big=True)
     out["gdn_fwd_channels_last"] = {"shape": list(x.shape), "bytes": 8 * n, "ms": t * 1e3, "gbs": 8 * n / t / 1e9}
     xcr = xc.clone().requires_grad_(True)
     yc = F.gdn(xcr, beta, w, False)
-    t = time_it(lambda: torch.autograd.grad(yc, (xcr, beta, w), gc, retain_graph=True))
+    t = time_it(lambda: torch.autograd.grad(yc, (xcr, beta, w), gc, retain_graph=True), big=True)
     out["gdn_bwd_channels_last"] = {"shape": list(x.shape), "bytes": 12 * n, "ms": t * 1e3, "gbs": 12 * n / t / 1e9}
     del x, g, xr, y, xc, gc, xcr, yc
     # likelihood kernel: the step's latent is tiny (launch-latency bound); the roofline figure is quoted on the top of the
@@ -452,7 +483,7 @@ def kernel_rooflines(cfg, dev, channels_last=True):
         yl = torch.randn(*shape, device=dev) * 3
         sg = torch.exp(torch.randn(shape[0], shape[1], 1, 1, device=dev))
         nu = torch.exp(torch.randn(shape[0], shape[1], 1, 1, device=dev) + 1.5)
-        t = time_it(lambda: F.bottleneck(yl, sg, nu, quant="noise"))
+        t = time_it(lambda: F.bottleneck(yl, sg, nu, quant="noise"), big=yl.numel() * 12 >= (512 << 20))
         ne = yl.numel()
         out[tag] = {"shape": list(shape), "bytes": 12 * ne, "ms": t * 1e3, "gbs": 12 * ne / t / 1e9}
         if tag == "k1_fwd_sweep_top":
@@ -461,14 +492,14 @@ def kernel_rooflines(cfg, dev, channels_last=True):
             yr, sr, nr = yl.clone().requires_grad_(True), sg.clone().requires_grad_(True), nu.clone().requires_grad_(True)
             yt, _, bits = F.bottleneck(yr, sr, nr, quant="noise")
             gb, gy = torch.ones_like(bits), torch.randn_like(yt)
-            t = time_it(lambda: torch.autograd.grad((bits, yt), (yr, sr, nr), (gb, gy), retain_graph=True))
+            t = time_it(lambda: torch.autograd.grad((bits, yt), (yr, sr, nr), (gb, gy), retain_graph=True), big=True)
             out["k1_bwd_sweep_top"] = {"shape": list(shape), "bytes": 12 * ne, "ms": t * 1e3, "gbs": 12 * ne / t / 1e9}
             del yr, yt, gy
             ss, ns = sg.expand_as(yl).contiguous(), nu.expand_as(yl).contiguous()
-            t = time_it(lambda: F.bottleneck(yl, ss, ns, quant="noise"))
+            t = time_it(lambda: F.bottleneck(yl, ss, ns, quant="noise"), big=True)
             out["k1_fwd_spatial_sweep_top"] = {"shape": list(shape), "bytes": 20 * ne, "ms": t * 1e3, "gbs": 20 * ne / t / 1e9}
             del ss, ns
-            t = time_it(lambda: F.bottleneck(yl, sg, nu, quant="noise", lik="cdf_diff"), reps=5)
+            t = time_it(lambda: F.bottleneck(yl, sg, nu, quant="noise", lik="cdf_diff"), reps=5, big=True)
             row = {"shape": list(shape), "bytes": 12 * ne, "ms": t * 1e3, "gbs": 12 * ne / t / 1e9, "bound": "sfu/issue (not hbm)",
                    "gelem_per_s": ne / t / 1e9}
             pipes = _committed("ncu_pipes_cdfdiff.json")
@@ -488,14 +519,14 @@ def kernel_rooflines(cfg, dev, channels_last=True):
         xd = torch.randn(Bd, Cd, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
         gm = torch.sqrt(torch.rand(Cd, Cd, device=dev) * 0.02 + torch.eye(Cd, device=dev) * 0.1 + 2.0 ** -18)
         bd = torch.sqrt(torch.rand(Cd, device=dev) + 0.5)
-        t = time_it(lambda: F.gdn_dense(xd, bd, gm, False))
+        t = time_it(lambda: F.gdn_dense(xd, bd, gm, False), big=True)
         nd = xd.numel()
         out[f"gdn_dense_fwd_tcgen05_c{Cd}"] = {"shape": list(xd.shape), "bytes": 8 * nd, "ms": t * 1e3, "gbs": 8 * nd / t / 1e9,
                                                "tf32_mma_tflops": 4.0 * Cd * nd / t / 1e12}
         xr, br, gr = xd.clone().requires_grad_(True), bd.clone().requires_grad_(True), gm.clone().requires_grad_(True)
         yv = F.gdn_dense(xr, br, gr, False)
         go = torch.randn_like(yv)
-        t = time_it(lambda: torch.autograd.grad(yv, (xr, br, gr), go, retain_graph=True), reps=5)
+        t = time_it(lambda: torch.autograd.grad(yv, (xr, br, gr), go, retain_graph=True), reps=5, big=True)
         out[f"gdn_dense_bwd_tcgen05_c{Cd}"] = {"shape": list(xd.shape), "bytes": 12 * nd, "ms": t * 1e3, "gbs": 12 * nd / t / 1e9,
                                                "note": "dx, d(beta), d(gamma): all launches of the backward"}
         del xd, xr, yv, go
@@ -521,7 +552,7 @@ def kernel_rooflines(cfg, dev, channels_last=True):
             "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic, "traffic_source": tsrc, "registers_per_thread": regs,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"],
             "timing": "CUDA events on the launching stream around the whole backward of the site (main kernel + the per-channel "
-                      "finalize), L2 flushed before each of 10 repetitions, a queued spin lets the host run ahead; median"}
+                      "finalize); 10 back-to-back repetitions of a 1.6 GB working set (13 x the L2: no flush needed, none done), a queued spin lets the host run ahead; median"}
     return roof, out
 
 

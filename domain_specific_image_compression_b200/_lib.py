@@ -41,6 +41,9 @@ PROTOTYPES = {
     "sic_gdn_dense_bwd": (_i, [_p, _p, _p, _p, _l, _i, _i, _p, _p, _p, _p, _i, _p]),
     "sic_gdn_dense_dgamma_workspace_bytes": (_z, [_l, _i]),
     "sic_gdn_dense_dgamma": (_i, [_p, _p, _l, _i, _p, _p, _z, _p]),
+    "sic_conv0_gdn_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "sic_conv0_gdn_bwd_workspace_bytes": (_z, [_i, _i, _i, _i]),
+    "sic_conv0_gdn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "sic_hyper_tail_save_floats": (_z, [_i, _i, _i]),
     "sic_hyper_tail_scratch_floats": (_z, [_i, _i, _i]),
     "sic_hyper_tail_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p]),

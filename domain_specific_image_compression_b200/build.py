@@ -31,6 +31,7 @@ SOURCES = [
     ("gdn_dense_ws.cu", []),
     ("gdn_dense_bwd.cu", []),
     ("gdn_dense_dgamma.cu", []),
+    ("conv0_gdn.cu", []),
     ("msssim.cu", []),
     ("hyper_tail.cu", []),
     ("tables.cu", ["-fmad=false"]),

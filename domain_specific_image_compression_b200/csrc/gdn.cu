@@ -11,37 +11,16 @@
 //
 // Forward uses only __f*_rn intrinsics so ptxas cannot contract mul+add into an FMA: a fused beta+gamma*x2 differs in
 // the last bit and would flip round() on latents that sit on a half-integer.
-#include "common.cuh"
+#include "gdn_math.cuh"
 
 namespace sic {
 namespace {
 
-constexpr float kOffset = 3.814697265625e-06f;  // 2^-18, layers.py:8
+using namespace gdnm;
+
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;
 constexpr int kChunk4 = 2048;  // float4 per backward unit (8192 elements)
-
-__device__ __forceinline__ void eff_params(const float *__restrict__ beta_param, const float *__restrict__ gamma_weight, int c,
-                                           float &beta, float &gamma) {
-    float b = __ldg(beta_param + c), w = __ldg(gamma_weight + c);
-    beta = __fadd_rn(__fmul_rn(b, b), -kOffset);   // layers.py:20
-    gamma = __fadd_rn(__fmul_rn(w, w), -kOffset);  // layers.py:21
-}
-
-// optional fused conv bias: PyTorch runs conv (no bias) -> add_(bias) -> GDN as three passes; the add is folded in here
-// (rn(x + b), the same rounding) and its gradient (sum of dx per channel) comes out of the backward's reduction for free.
-// -0.0f is the neutral element that keeps every bit of x, including the sign of zero.
-__device__ __forceinline__ float load_bias(const float *__restrict__ bias, int c) { return bias != nullptr ? __ldg(bias + c) : -0.0f; }
-
-template <bool INVERSE>
-__device__ __forceinline__ float gdn1(float xin, float bias, float beta, float gamma) {
-    float x = __fadd_rn(xin, bias);
-    float x2 = __fmul_rn(x, x);
-    float p = __fmul_rn(gamma, x2);
-    float s = __fadd_rn(beta, p);
-    float d = __fsqrt_rn(s);
-    return INVERSE ? __fmul_rn(x, d) : __fdiv_rn(x, d);
-}
 
 // NCHW vector path: one CTA per (plane, chunk of kChunk4 float4) so that beta/gamma are CTA constants and the only
 // per-vector integer work is one add (the first version divided every vector index by HW/4 and C: 15 of its 30
@@ -147,26 +126,7 @@ __global__ void __launch_bounds__(kThreads, 5) gdn_fwd_nhwc_kernel(const float4 
     }
 }
 
-// ---- backward ------------------------------------------------------------------------------------------------------
-// GDN : y = x/d    dx = g*beta/d^3            h = -1/2 g x / d^3
-// IGDN: y = x*d    dx = g*(s + gamma x^2)/d   h = +1/2 g x / d          dbeta_c = sum h ; dgamma_c = sum h x^2
-template <bool INVERSE>
-__device__ __forceinline__ void gdn_bwd1(float x, float g, float beta, float gamma, float &dx, float &hb, float &hg) {
-    float x2 = x * x;
-    float gx2 = gamma * x2;
-    float s = beta + gx2;
-    float r = rsqrtf(s);
-    if (INVERSE) {
-        dx = g * (s + gx2) * r;
-        hb = 0.5f * g * x * r;
-    } else {
-        float r3 = r * r * r;
-        dx = g * beta * r3;
-        hb = -0.5f * g * x * r3;
-    }
-    hg = hb * x2;
-}
-
+// ---- backward (per-element formulas: gdn_math.cuh) ---------------------------------------------------------------
 __device__ __forceinline__ void block_sum3(float &a, float &b, float &c) {
     __shared__ float sa[kThreads / 32], sb[kThreads / 32], sc[kThreads / 32];
     a = warp_sum(a);
@@ -316,44 +276,34 @@ __global__ void __launch_bounds__(kThreads, 4) gdn_bwd_nhwc_kernel(const float4 
 // load per iteration the fold alone took ~35 us (r02c: 246 us of main kernel became 281 us per site).  512 threads, four independent
 // loads in flight per thread and array: the fold is back to a few microseconds.  Summation order is fixed by (thread, position).
 constexpr int kFinThreads = 512;
+// grid (C, 3): blockIdx.y = 0 d(beta), 1 d(gamma), 2 d(bias) - three CTAs per channel instead of one (r02d: 9.1 us for the 12.6 MB of
+// partials of the 256^2 site on 128 CTAs; the fold is latency-bound, so it wants every SM)
 __global__ void __launch_bounds__(kFinThreads) gdn_bwd_finalize_kernel(const float *__restrict__ part, const float *__restrict__ beta_param,
                                                                      const float *__restrict__ gamma_weight, int C, long P,
                                                                      float *__restrict__ dbeta_param, float *__restrict__ dgamma_weight,
                                                                      float *__restrict__ dbias) {
-    const int c = blockIdx.x;
-    const float *pb = part + (long)c * P, *pg = part + (long)C * P + (long)c * P, *px = part + 2 * (long)C * P + (long)c * P;
-    double sb = 0.0, sg = 0.0, sx = 0.0;
+    const int c = blockIdx.x, which = blockIdx.y;
+    float *dst = which == 0 ? dbeta_param : (which == 1 ? dgamma_weight : dbias);
+    if (dst == nullptr) return;
+    const float *pp = part + (long)which * C * P + (long)c * P;
+    double s = 0.0;
     long i = threadIdx.x;
     for (; i + 3 * kFinThreads < P; i += 4 * kFinThreads) {
-        float b0 = __ldcs(pb + i), b1 = __ldcs(pb + i + kFinThreads), b2 = __ldcs(pb + i + 2 * kFinThreads), b3 = __ldcs(pb + i + 3 * kFinThreads);
-        float g0 = __ldcs(pg + i), g1 = __ldcs(pg + i + kFinThreads), g2 = __ldcs(pg + i + 2 * kFinThreads), g3 = __ldcs(pg + i + 3 * kFinThreads);
-        float x0 = __ldcs(px + i), x1 = __ldcs(px + i + kFinThreads), x2 = __ldcs(px + i + 2 * kFinThreads), x3 = __ldcs(px + i + 3 * kFinThreads);
-        sb += ((double)b0 + (double)b1) + ((double)b2 + (double)b3);
-        sg += ((double)g0 + (double)g1) + ((double)g2 + (double)g3);
-        sx += ((double)x0 + (double)x1) + ((double)x2 + (double)x3);
+        float v0 = __ldcs(pp + i), v1 = __ldcs(pp + i + kFinThreads), v2 = __ldcs(pp + i + 2 * kFinThreads), v3 = __ldcs(pp + i + 3 * kFinThreads);
+        s += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
     }
-    for (; i < P; i += kFinThreads) {
-        sb += (double)__ldcs(pb + i);
-        sg += (double)__ldcs(pg + i);
-        sx += (double)__ldcs(px + i);
-    }
-    __shared__ double shb[kFinThreads / 32], shg[kFinThreads / 32], shx[kFinThreads / 32];
-    sb = warp_sum(sb);
-    sg = warp_sum(sg);
-    sx = warp_sum(sx);
-    if ((threadIdx.x & 31) == 0) { shb[threadIdx.x >> 5] = sb; shg[threadIdx.x >> 5] = sg; shx[threadIdx.x >> 5] = sx; }
+    for (; i < P; i += kFinThreads) s += (double)__ldcs(pp + i);
+    __shared__ double sh[kFinThreads / 32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x < 32) {
-        sb = threadIdx.x < kFinThreads / 32 ? shb[threadIdx.x] : 0.0;
-        sg = threadIdx.x < kFinThreads / 32 ? shg[threadIdx.x] : 0.0;
-        sx = threadIdx.x < kFinThreads / 32 ? shx[threadIdx.x] : 0.0;
-        sb = warp_sum(sb);
-        sg = warp_sum(sg);
-        sx = warp_sum(sx);
+        s = threadIdx.x < kFinThreads / 32 ? sh[threadIdx.x] : 0.0;
+        s = warp_sum(s);
         if (threadIdx.x == 0) {
-            if (dbeta_param) dbeta_param[c] = (float)(sb * 2.0 * (double)beta_param[c]);
-            if (dgamma_weight) dgamma_weight[c] = (float)(sg * 2.0 * (double)gamma_weight[c]);
-            if (dbias) dbias[c] = (float)sx;
+            if (which == 0) s *= 2.0 * (double)beta_param[c];
+            else if (which == 1) s *= 2.0 * (double)gamma_weight[c];
+            dst[c] = (float)s;
         }
     }
 }
@@ -366,7 +316,7 @@ inline int nhwc_iters(long n4, int per_pass, int max_iters) {
     long it = n4 / ((long)per_pass * sm_count() * 8);
     return (int)(it < 1 ? 1 : (it > max_iters ? max_iters : it));
 }
-inline int nhwc_bwd_iters(long n4, int threads) { return nhwc_iters(n4, threads * kBwdNhwcU, n4 > (64L << 20) ? 16 : 8); }
+inline int nhwc_bwd_iters(long n4, int threads) { return nhwc_iters(n4, threads * kBwdNhwcU, n4 > (16L << 20) ? 16 : 8); }
 inline long nhwc_bwd_grid(long n4, int threads) {
     const long chunk = (long)threads * kBwdNhwcU * nhwc_bwd_iters(n4, threads);
     return (n4 + chunk - 1) / chunk;
@@ -457,7 +407,7 @@ extern "C" int sic_gdn_bwd(const float *x, const float *bias, const float *g, co
         if (inverse) gdn_bwd_nhwc_kernel<true><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, iters, (float4 *)dx, part);
         else gdn_bwd_nhwc_kernel<false><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, iters, (float4 *)dx, part);
         SIC_CHECK_LAUNCH("sic_gdn_bwd (nhwc)");
-        gdn_bwd_finalize_kernel<<<C, kFinThreads, 0, st>>>(part, beta_param, gamma_weight, C, (long)grid, dbeta_param, dgamma_weight, dbias);
+        gdn_bwd_finalize_kernel<<<dim3(C, 3), kFinThreads, 0, st>>>(part, beta_param, gamma_weight, C, (long)grid, dbeta_param, dgamma_weight, dbias);
         SIC_CHECK_LAUNCH("sic_gdn_bwd finalize");
         return 0;
     }
@@ -473,7 +423,7 @@ extern "C" int sic_gdn_bwd(const float *x, const float *bias, const float *g, co
         else gdn_bwd_kernel<false, false><<<(unsigned)units, kThreads, 0, st>>>(x, bias, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
     }
     SIC_CHECK_LAUNCH("sic_gdn_bwd");
-    gdn_bwd_finalize_kernel<<<C, kFinThreads, 0, st>>>(part, beta_param, gamma_weight, C, (long)B * chunks, dbeta_param, dgamma_weight, dbias);
+    gdn_bwd_finalize_kernel<<<dim3(C, 3), kFinThreads, 0, st>>>(part, beta_param, gamma_weight, C, (long)B * chunks, dbeta_param, dgamma_weight, dbias);
     SIC_CHECK_LAUNCH("sic_gdn_bwd finalize");
     return 0;
 }

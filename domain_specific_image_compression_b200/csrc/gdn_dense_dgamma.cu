@@ -269,6 +269,10 @@ extern "C" int sic_gdn_dense_dgamma(const float *x, const float *h, long positio
     SIC_CHECK_ARG(x && h && dgamma_eff && workspace, "sic_gdn_dense_dgamma: null pointer");
     SIC_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)h & 15) == 0 && ((uintptr_t)workspace & 15) == 0,
                   "sic_gdn_dense_dgamma: tensors must be 16-byte aligned");
+    if (!(C == 32 || C == 64 || C == 96 || C == 128 || C == 192)) {      // before the workspace check: an unsupported C is the cause
+        set_error("sic_gdn_dense_dgamma: C=%d unsupported (C in {32,64,96,128,192})", C);
+        return SIC_E_UNSUPPORTED;
+    }
     if (workspace_bytes < sic_gdn_dense_dgamma_workspace_bytes(positions, C)) {
         set_error("sic_gdn_dense_dgamma: workspace %zu < %zu bytes", workspace_bytes, sic_gdn_dense_dgamma_workspace_bytes(positions, C));
         return SIC_E_WORKSPACE;

@@ -333,6 +333,79 @@ def gdn_dense(x: torch.Tensor, beta_param: torch.Tensor, gamma_param: torch.Tens
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# N2: first analysis layer (conv 3 -> C, 3x3 + bias + GDN) as one kernel
+CONV0_CHANNELS = (32, 64, 96, 128, 192)
+
+
+class _Conv0GDN(torch.autograd.Function):
+    """layers.py:49-51 fused (csrc/conv0_gdn.cu).  The C x H x W intermediate is never stored: the backward recomputes it from the
+    image on the tensor core and contracts dv with the im2col patches there too.  The image itself gets no gradient."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, x, weight, bias, beta_param, gamma_weight, want_v: bool):
+        lib = _lib.load()
+        if not isinstance(x, torch.Tensor) or not x.is_cuda:
+            raise _lib.SicError("conv0_gdn: expected a CUDA tensor — this package has no CPU path (the CPU oracle is oracle/, test only)")
+        if x.dim() != 4 or x.shape[1] != 3 or x.dtype != torch.float32:
+            raise _lib.SicError(f"conv0_gdn: expected a float32 [B,3,H,W] image, got {tuple(x.shape)} {x.dtype}")
+        if ctx.needs_input_grad[0]:
+            raise _lib.SicError("conv0_gdn: the fused first layer does not return a gradient for the image")
+        B, _, H, W = x.shape
+        C = weight.shape[0]
+        if tuple(weight.shape) != (C, 3, 3, 3) or C not in CONV0_CHANNELS:
+            raise _lib.SicError(f"conv0_gdn: weight {tuple(weight.shape)} is not [C,3,3,3] with C in {CONV0_CHANNELS}")
+        xh = x.permute(0, 2, 3, 1).contiguous()                                   # [B,H,W,3]; a view when x is channels_last
+        wk = _require_cuda_f32(weight, "weight").permute(0, 2, 3, 1).contiguous()  # [C,kh,kw,cin]
+        bias = None if bias is None else _require_cuda_f32(bias, "bias")
+        beta_param = _require_cuda_f32(beta_param, "beta")
+        ctx.w_shape = gamma_weight.shape
+        gamma_weight = _require_cuda_f32(gamma_weight.reshape(-1), "gamma_conv.weight")
+        if beta_param.numel() != C or gamma_weight.numel() != C or (bias is not None and bias.numel() != C):
+            raise _lib.SicError(f"conv0_gdn: parameters do not match C={C}")
+        y = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+        v = torch.empty_like(y) if want_v else None
+        with torch.cuda.device(x.device):
+            _launch(lib.sic_conv0_gdn_fwd(_ptr(xh), _ptr(wk), _ptr(bias), _ptr(beta_param), _ptr(gamma_weight), B, H, W, C, _ptr(y), _ptr(v),
+                                          _stream()), "sic_conv0_gdn_fwd")
+        ctx.save_for_backward(xh, wk, bias, beta_param, gamma_weight)
+        ctx.geom = (B, H, W, C)
+        ctx.set_materialize_grads(False)
+        if want_v:
+            ctx.mark_non_differentiable(v)
+        return y, v
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g, _gv):
+        lib = _lib.load()
+        xh, wk, bias, beta_param, gamma_weight = ctx.saved_tensors
+        B, H, W, C = ctx.geom
+        g = _dense_layout(g.contiguous(memory_format=torch.channels_last), "grad_output")[0]
+        dev = xh.device
+        dw = torch.empty((C, 3, 3, 3), dtype=torch.float32, device=dev)           # (kh, kw, cin) order
+        dbias = torch.empty_like(bias) if bias is not None else None
+        dbeta, dgamma = torch.empty_like(beta_param), torch.empty_like(gamma_weight)
+        ws = _workspace(dev, lib.sic_conv0_gdn_bwd_workspace_bytes(B, H, W, C), "scratch")
+        with torch.cuda.device(dev):
+            _lib.check(lib.sic_conv0_gdn_bwd(_ptr(xh), _ptr(wk), _ptr(bias), _ptr(beta_param), _ptr(gamma_weight), _ptr(g), B, H, W, C,
+                                             _ptr(dw), _ptr(dbias), _ptr(dbeta), _ptr(dgamma), _ptr(ws), ws.numel(), _stream()),
+                       "sic_conv0_gdn_bwd")
+        global launch_count
+        launch_count += 2
+        return None, dw.permute(0, 3, 1, 2), dbias, dbeta, dgamma.view(ctx.w_shape), None
+
+
+def conv0_gdn(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], beta_param: torch.Tensor,
+              gamma_weight: torch.Tensor, return_v: bool = False):
+    """First analysis layer in one kernel (N2): GDN(conv2d(x, weight, bias, stride 1, padding 1)) for a [B,3,H,W] image and a
+    [C,3,3,3] weight; returns a channels_last [B,C,H,W] tensor (and the pre-GDN activation with return_v=True, tests only).
+    Tolerance-only training path (fp32-accurate tensor-core convolution, rsqrt GDN): see include/sic.h."""
+    y, v = _Conv0GDN.apply(x, weight, bias, beta_param, gamma_weight, bool(return_v))
+    return (y, v) if return_v else y
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # N4: tail of the hyper-synthesis transform
 class _HyperTail(torch.autograd.Function):
     @staticmethod

@@ -39,6 +39,20 @@ class GDN(nn.Module):
 FUSE_CONV_BIAS = True      # fold each convolution's bias add (and its gradient reduction) into the following GDN kernel
 
 
+# Opt-in (bench.py and FlatTrainer switch it on): in TRAINING mode run conv 3->N 3x3 + bias + GDN of g_a as ONE kernel
+# (F_sic.conv0_gdn: no C x H x W intermediate, backward recomputes it).  The fused convolution is fp32-accurate but not bit-identical
+# to cuDNN's, so the library default keeps the cuDNN + K2 path whose latents are pinned bit for bit against the reference, and eval /
+# compress never use the fused layer.
+FUSE_FIRST_LAYER = False
+
+
+def _first_layer_fusable(m, nxt, x, training):
+    return (FUSE_FIRST_LAYER and training and isinstance(m, nn.Conv2d) and isinstance(nxt, GDN) and not nxt.dense and not nxt.inverse
+            and m.in_channels == 3 and m.kernel_size == (3, 3) and m.stride == (1, 1) and m.padding == (1, 1) and m.dilation == (1, 1)
+            and m.groups == 1 and m.padding_mode == "zeros" and m.out_channels in F_sic.CONV0_CHANNELS
+            and x.is_cuda and x.dtype == torch.float32 and not x.requires_grad and PAD_RGB_CHANNELS <= 3)
+
+
 PAD_RGB_CHANNELS = 0       # 4 or 8: run the 3-channel first conv / last transposed conv with zero-padded channels (see _rgb_padded)
 
 
@@ -77,6 +91,10 @@ def _run(seq: nn.Sequential, x):
     while i < len(mods):
         m = mods[i]
         nxt = mods[i + 1] if i + 1 < len(mods) else None
+        if _first_layer_fusable(m, nxt, x, seq.training):
+            x = F_sic.conv0_gdn(x, m.weight, m.bias, nxt.beta, nxt.gamma_conv.weight)
+            i += 2
+            continue
         padded = _rgb_padded(m, x) if (PAD_RGB_CHANNELS > 3 and x.is_cuda) else None
         if padded is not None:
             t, bias = padded

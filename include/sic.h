@@ -145,6 +145,25 @@ int sic_gdn_dense_dgamma(const float *x, const float *h, long positions, int C, 
                          size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * N2  first analysis layer as ONE kernel: conv 3 -> C, 3x3, stride 1, zero padding 1 (layers.py:49-50, `conv(3, N, 3, 1)`) + bias +
+ * GDN (layers.py:51, arithmetic :19-27).  Replaces cuDNN conv (legacy non-tensor-core engine: 3 channels) + add_(bias) + K2, and in
+ * the backward K2's backward + cuDNN wgrad; the C x 256 x 256 intermediate is neither written nor read (csrc/conv0_gdn.cu).
+ *   x [B, H, W, 3]: the image, CHANNELS-LAST.  w [C, 3, 3, 3] in (kh, kw, cin) order = a channels_last [C,3,3,3] weight's memory.
+ *   bias (nullable) [C], beta_param [C], gamma_weight [C]: stored parameters as for sic_gdn_fwd.
+ *   y [B, H, W, C] channels-last.  v_out (nullable): conv + bias before the GDN, same layout (tests).
+ *   tcgen05 kind::tf32 with exact hi/lo splits of weights and taps: the convolution is evaluated to fp32 accuracy (2^-22 relative);
+ *   GDN as v * rsqrt(beta + gamma v^2).  Tolerance-only (training) path: the bit-exact latents of eval/compress stay on cuDNN + K2.
+ * bwd: grad_y [B, H, W, C] -> dw [C, 27] (same order as w), dbias (nullable), dbeta_param, dgamma_weight (chain rule through the squared
+ *   re-parameterisation applied); v is recomputed from the image, the image gets no gradient.  Deterministic (fixed-order binary64
+ *   fold of per-CTA partials).  workspace: sic_conv0_gdn_bwd_workspace_bytes bytes, any content.  C in {32, 64, 96, 128, 192}. */
+int sic_conv0_gdn_fwd(const float *x, const float *w, const float *bias, const float *beta_param, const float *gamma_weight, int B,
+                      int H, int W, int C, float *y, float *v_out, void *stream);
+size_t sic_conv0_gdn_bwd_workspace_bytes(int B, int H, int W, int C);
+int sic_conv0_gdn_bwd(const float *x, const float *w, const float *bias, const float *beta_param, const float *gamma_weight,
+                      const float *grad_y, int B, int H, int W, int C, float *dw, float *dbias, float *dbeta_param,
+                      float *dgamma_weight, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * N4  tail of the hyper-synthesis transform in one launch: layers.py:141-152 (AdaptiveAvgPool2d(1) -> mlp_sigma / mlp_nu, two 1x1
  * convolutions with a ReLU each) + model.py:54-55 (exp, mean over an already constant map, clamp of nu); the decoder runs the same
  * chain at eval_selfcontained_entropy.py:99-106 between the z decode and the y tables.

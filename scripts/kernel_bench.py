@@ -13,6 +13,7 @@ ap.add_argument("--quick", action="store_true")
 ap.add_argument("--only", default="")
 ap.add_argument("--json", default="")
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--eager-timing", action="store_true")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 try:
@@ -21,11 +22,33 @@ except OSError:
     PEAK = 6650.0
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-def time_it(fn, reps=args.reps):
+def time_it(fn, reps=args.reps, nbytes=0):
+    """Kernels that stream >= 256 MB (2 x the 126 MB L2, walked front to back) are timed without a flush: "inputs larger than L2"
+    (B200_PROFILING.md).  Flushing by writing 256 MB leaves 126 MB of dirty lines whose write-back is billed to the kernel.  Those
+    launches are captured `reps` times into one CUDA graph and the replay is timed (launch gaps as inside the step's own graph,
+    not Python's dispatch time); --eager-timing keeps the per-launch event pairs."""
     for _ in range(3): fn()
+    big = nbytes >= (256 << 20)
+    if big and not args.eager_timing:
+        try:
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for _ in range(reps): fn()
+            gr.replay(); ts = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) / reps)
+            del gr
+            ts.sort()
+            return ts[len(ts) // 2] * 1e-3
+        except Exception as e:
+            print(f"graph timing unavailable ({type(e).__name__}: {str(e)[:100]}); eager", flush=True)
+            torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
-        flush.zero_()
+        if not big: flush.zero_()
         # a queued spin (~0.2 ms) lets the host run ahead of the device: without it the GPU sits idle between e0 and the kernel
         # while Python is still dispatching (~45 us for an autograd backward) and the idle time is billed to the kernel (r01:
         # gdn_bwd nhwc 295 us by events vs 252 us under ncu; every backward below 43 us "floor")
@@ -52,17 +75,17 @@ if args.only in ("", "k1"):
             if n * 4 * 6 > 60e9: continue
             y = torch.randn(B, C, h, w, device=dev) * 3
             sg = torch.exp(torch.randn(B, C, 1, 1, device=dev)); nu = torch.exp(torch.randn(B, C, 1, 1, device=dev) + 1.5)
-            report("k1_fwd density bcast noise", y.shape, 12 * n, time_it(lambda: F.bottleneck(y, sg, nu, quant="noise")))
-            report("k1_fwd density bcast round", y.shape, 12 * n, time_it(lambda: F.bottleneck(y, sg, nu, quant="round")))
+            report("k1_fwd density bcast noise", y.shape, 12 * n, time_it(lambda: F.bottleneck(y, sg, nu, quant="noise"), nbytes=12 * n))
+            report("k1_fwd density bcast round", y.shape, 12 * n, time_it(lambda: F.bottleneck(y, sg, nu, quant="round"), nbytes=12 * n))
             yr = y.clone().requires_grad_(True); sr = sg.clone().requires_grad_(True); nr = nu.clone().requires_grad_(True)
             yt, nll, bits = F.bottleneck(yr, sr, nr, quant="noise")
             gb = torch.ones_like(bits); gy = torch.randn_like(yt)
-            report("k1_bwd density bcast (bits+dy~)", y.shape, 12 * n, time_it(lambda: torch.autograd.grad((bits, yt), (yr, sr, nr), (gb, gy), retain_graph=True)))
+            report("k1_bwd density bcast (bits+dy~)", y.shape, 12 * n, time_it(lambda: torch.autograd.grad((bits, yt), (yr, sr, nr), (gb, gy), retain_graph=True), nbytes=12 * n))
             if B == 16 or args.quick:
                 ss = sg.expand_as(y).contiguous(); ns = nu.expand_as(y).contiguous()
-                report("k1_fwd density spatial noise", y.shape, 20 * n, time_it(lambda: F.bottleneck(y, ss, ns, quant="noise")))
+                report("k1_fwd density spatial noise", y.shape, 20 * n, time_it(lambda: F.bottleneck(y, ss, ns, quant="noise"), nbytes=20 * n))
                 try:
-                    report("k1_fwd cdf_diff bcast noise", y.shape, 12 * n, time_it(lambda: F.bottleneck(y, sg, nu, quant="noise", lik="cdf_diff")))
+                    report("k1_fwd cdf_diff bcast noise", y.shape, 12 * n, time_it(lambda: F.bottleneck(y, sg, nu, quant="noise", lik="cdf_diff"), nbytes=12 * n))
                 except Exception as e:
                     print("cdf_diff unavailable:", str(e)[:80])
                 del ss, ns
@@ -79,10 +102,10 @@ if args.only in ("", "gdn"):
                 n = x.numel()
                 for inv in (False, True):
                     nm = "igdn" if inv else "gdn"
-                    report(f"{nm}_fwd {tag}", x.shape, 8 * n, time_it(lambda: F.gdn(x, beta, w, inv)))
+                    report(f"{nm}_fwd {tag}", x.shape, 8 * n, time_it(lambda: F.gdn(x, beta, w, inv), nbytes=8 * n))
                     xr = x.clone().requires_grad_(True)
                     yv = F.gdn(xr, beta, w, inv)
-                    report(f"{nm}_bwd {tag}", x.shape, 12 * n, time_it(lambda: torch.autograd.grad(yv, (xr, beta, w), g, retain_graph=True)))
+                    report(f"{nm}_bwd {tag}", x.shape, 12 * n, time_it(lambda: torch.autograd.grad(yv, (xr, beta, w), g, retain_graph=True), nbytes=12 * n))
                     del xr, yv
                 del x, g
 if args.only in ("", "dense"):
@@ -96,7 +119,7 @@ if args.only in ("", "dense"):
                 continue
             for inv in (False, True):
                 try:
-                    t = time_it(lambda: F.gdn_dense(x, beta, gm, inv, variant))
+                    t = time_it(lambda: F.gdn_dense(x, beta, gm, inv, variant), nbytes=8 * n)
                 except Exception as e:   # keep the sweep going if one variant is broken on this box
                     print(f"dense {vname} inv={inv}: FAILED {e}", flush=True)
                     continue
@@ -110,13 +133,39 @@ if args.only in ("", "dense"):
             br, gr = beta.clone().requires_grad_(True), gm.clone().requires_grad_(True)
             yv = F.gdn_dense(xr, br, gr, False)
             go = torch.randn_like(yv)
-            t = time_it(lambda: torch.autograd.grad(yv, (xr, br, gr), go, retain_graph=True), reps=5)
+            t = time_it(lambda: torch.autograd.grad(yv, (xr, br, gr), go, retain_graph=True), reps=5, nbytes=12 * n)
             report("gdn_dense_bwd tcgen05 3-pass", x.shape, 12 * n, t)
-            t = time_it(lambda: torch.autograd.grad(yv, (xr, br), go, retain_graph=True), reps=5)
+            t = time_it(lambda: torch.autograd.grad(yv, (xr, br), go, retain_graph=True), reps=5, nbytes=12 * n)
             report("gdn_dense_bwd tcgen05 (dx, dbeta only)", x.shape, 12 * n, t)
             del xr, yv, go
         except Exception as e:
             print(f"dense bwd: FAILED {e}", flush=True)
         del x
+if args.only in ("", "conv0"):
+    # N2: first analysis layer fused (conv 3->C 3x3 + bias + GDN, one kernel each way) vs the unfused cuDNN conv + GDN kernel.
+    # Algorithmic bytes: forward = image in + y out; backward = image + grad_y in (parameter gradients out are KBs).
+    import torch.nn.functional as TF
+    torch.backends.cudnn.benchmark = True
+    for (B, C, H, W) in [(16, 128, 256, 256), (8, 192, 256, 256)]:
+        try:
+            x = torch.rand(B, 3, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+            w = (torch.randn(C, 3, 3, 3, device=dev) * 0.3).contiguous(memory_format=torch.channels_last)
+            bias = torch.randn(C, device=dev) * 0.2
+            beta = torch.sqrt(torch.rand(C, device=dev) + 0.5); gw = torch.sqrt(torch.rand(C, 1, 1, 1, device=dev) * 0.3 + 0.01)
+            n = B * C * H * W
+            fb, bb = 4 * n + 4 * x.numel(), 4 * n + 4 * x.numel()
+            report("conv0+gdn fused fwd (tcgen05)", (B, C, H, W), fb, time_it(lambda: F.conv0_gdn(x, w, bias, beta, gw), nbytes=fb))
+            ps = [t.clone().requires_grad_(True) for t in (w, bias, beta, gw)]
+            y = F.conv0_gdn(x, *ps); go = torch.randn_like(y)
+            report("conv0+gdn fused bwd (tcgen05 x2)", (B, C, H, W), bb, time_it(lambda: torch.autograd.grad(y, ps, go, retain_graph=True), nbytes=bb))
+            del y
+            unf = lambda: F.gdn(TF.conv2d(x, w, None, 1, 1), beta, gw, False, bias=bias)
+            report("conv0 cuDNN + gdn kernel fwd", (B, C, H, W), fb, time_it(unf, nbytes=fb))
+            ps = [t.clone().requires_grad_(True) for t in (w, bias, beta, gw)]
+            y = F.gdn(TF.conv2d(x, ps[0], None, 1, 1), ps[2], ps[3], False, bias=ps[1])
+            report("conv0 cuDNN + gdn kernel bwd", (B, C, H, W), bb, time_it(lambda: torch.autograd.grad(y, ps, go, retain_graph=True), nbytes=bb))
+            del y, go, x
+        except Exception as e:
+            print(f"conv0 {B}x{C}: FAILED {type(e).__name__}: {e}", flush=True)
 if args.json:
     json.dump({"peak_gbs": PEAK, "rows": rows}, open(args.json, "w"), indent=1)

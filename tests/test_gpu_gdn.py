@@ -373,6 +373,8 @@ def test_dense_dgamma_kernel_vs_float64(C, P):
         assert rc == 0, lib.sic_last_error()
     ref = h.double().t() @ (x.double() ** 2)
     err = float((out.double() - ref).abs().max())
-    assert err <= 2e-6 * float(ref.abs().max()) + 1e-6, (err, float(ref.abs().max()))
-    assert lib.sic_gdn_dense_dgamma(vp(x), vp(h), P, 48, vp(out), vp(ws), ws.numel(), None) == -3       # SIC_E_UNSUPPORTED
-    assert lib.sic_gdn_dense_dgamma(vp(x), vp(h), P, C, vp(out), vp(ws), 0, None) == (-2 if nws else 0)  # SIC_E_WORKSPACE
+    # fp32 accumulation over up to 65536 positions in the tensor core: a few 1e-6 relative; the operand split itself is exact
+    assert err <= 1e-5 * float(ref.abs().max()) + 1e-6, (err, float(ref.abs().max()))
+    big = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    assert lib.sic_gdn_dense_dgamma(vp(x), vp(h), P, 48, vp(out), vp(big), big.numel(), None) == -3     # SIC_E_UNSUPPORTED
+    assert lib.sic_gdn_dense_dgamma(vp(x), vp(h), P, C, vp(out), vp(ws), 0, None) == -2                 # SIC_E_WORKSPACE
