@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--no-fuse-first-layer", action="store_true", help="keep g_a's first layer as cuDNN conv + GDN kernel (default: the fused "
                     "conv 3->N 3x3 + bias + GDN tcgen05 kernel, forward and backward: layers.FUSE_FIRST_LAYER)")
+    ap.add_argument("--no-fast-last-layer", action="store_true", help="keep g_s's last layer deconv(N,3) on cuDNN (default: library GEMM + "
+                    "the col2im / im2col gather kernels: layers.FAST_LAST_LAYER)")
     ap.add_argument("--pad-rgb", type=int, default=0, choices=[0, 4, 8], help="zero-pad the image-side channel axis of the first conv / "
                     "last transposed conv to 4 or 8 so cuDNN can use tensor-core kernels there (layers.PAD_RGB_CHANNELS; identity "
                     "in exact arithmetic, off by default)")
@@ -259,6 +261,7 @@ def run_ours(args):
     if args.pad_rgb:
         _layers.PAD_RGB_CHANNELS = args.pad_rgb
     _layers.FUSE_FIRST_LAYER = not (args.no_fuse_first_layer or args.pad_rgb or args.gdn == "dense" or args.nchw)
+    _layers.FAST_LAST_LAYER = not (args.no_fast_last_layer or args.pad_rgb or args.nchw)
     model = model.to(memory_format=fmt)
     trainer = FlatTrainer(model, lr=1e-4, betas=(0.9, 0.999), grad_clip=1.0, bucket_bytes=int(args.bucket_mb * (1 << 20)))
     x_dev = synthetic_batch(B, H, W, 42 + rank, dev).contiguous(memory_format=fmt)
@@ -375,7 +378,7 @@ def run_ours(args):
                        "l2": "per-step working set (>= 5 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "conv_math": "cuDNN fp32 with TF32 allowed (PyTorch default, as the reference)",
                        "activation_layout": "NCHW" if args.nchw else "channels_last", "launch": graph_note,
-                       "rgb_channel_padding": args.pad_rgb, "gdn": args.gdn, "fused_first_layer": bool(_layers.FUSE_FIRST_LAYER),
+                       "rgb_channel_padding": args.pad_rgb, "gdn": args.gdn, "fused_first_layer": bool(_layers.FUSE_FIRST_LAYER), "gemm_last_layer": bool(_layers.FAST_LAST_LAYER),
                        "gradient_buckets": [hi - lo for lo, hi, _, _ in trainer.buckets] if world > 1 else None,
                        "cudnn_benchmark": not args.no_cudnn_benchmark},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
@@ -416,35 +419,27 @@ def kernel_rooflines(cfg, dev, channels_last=True):
         reuse each other's lines and no flush is needed (B200_PROFILING.md: "either flush L2 or use inputs larger than L2").
         Flushing by WRITING 256 MB, as the small cases do, leaves the L2 full of dirty lines whose write-back (126 MB, ~8 % of a
         1.6 GB kernel) is then billed to the kernel under test: ncu, which invalidates instead, timed the same launches 7 % faster.
-        The `reps` launches are captured into ONE CUDA graph and the replay is timed with events on the replaying stream: the
-        launch-to-launch gap is then the one the kernel sees inside the step (which is itself replayed as a graph) instead of
-        Python's dispatch time.  Median of 5 replays / reps."""
+        The `reps` launches are queued back to back behind a ~1 ms device-side spin, so the host (45 us of Python per autograd
+        call) is a full queue ahead and the launch-to-launch gap is the device's own, as inside the step's CUDA graph; one event
+        pair around the batch, time / reps, median of 3 batches."""
         for _ in range(3):
             fn()
         if big:
-            try:
+            ts = []
+            for _ in range(3):
+                torch.cuda._sleep(2_000_000)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
                 torch.cuda.synchronize()
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr):
-                    for _ in range(reps):
-                        fn()
-                ts = []
-                gr.replay()
-                for _ in range(5):
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(); gr.replay(); e1.record()
-                    torch.cuda.synchronize()
-                    ts.append(e0.elapsed_time(e1) / reps)
-                del gr
-                ts.sort()
-                return ts[len(ts) // 2] * 1e-3
-            except Exception as e:                               # capture refused (allocator state, library call): eager timing below
-                print(f"[bench] kernel timing: graph capture failed ({type(e).__name__}: {str(e)[:120]}), timing eager launches", file=sys.stderr)
-                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) / reps)
+            ts.sort()
+            return ts[1] * 1e-3
         ts = []
         for _ in range(reps):
-            if not big:
-                flush.zero_()
+            flush.zero_()
             # a queued spin (~0.2 ms) lets the host run ahead: without it the GPU idles between e0 and the kernel while Python
             # (autograd dispatch, ~45 us for a backward) is still launching, and that idle time was being billed to the kernel
             torch.cuda._sleep(400_000)

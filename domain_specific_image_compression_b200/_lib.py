@@ -44,6 +44,8 @@ PROTOTYPES = {
     "sic_conv0_gdn_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "sic_conv0_gdn_bwd_workspace_bytes": (_z, [_i, _i, _i, _i]),
     "sic_conv0_gdn_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
+    "sic_deconv_rgb_col2im": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "sic_deconv_rgb_im2col": (_i, [_p, _i, _i, _i, _p, _p]),
     "sic_hyper_tail_save_floats": (_z, [_i, _i, _i]),
     "sic_hyper_tail_scratch_floats": (_z, [_i, _i, _i]),
     "sic_hyper_tail_fwd": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p]),

@@ -32,6 +32,7 @@ SOURCES = [
     ("gdn_dense_bwd.cu", []),
     ("gdn_dense_dgamma.cu", []),
     ("conv0_gdn.cu", []),
+    ("deconv_rgb.cu", []),
     ("msssim.cu", []),
     ("hyper_tail.cu", []),
     ("tables.cu", ["-fmad=false"]),

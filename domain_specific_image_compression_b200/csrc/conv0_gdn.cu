@@ -263,15 +263,16 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
                         }
                         float lo[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {             // GDN backward (gdn_math.cuh gdn_bwd1<false>) with the one-MUFU rsqrt
-                            const float v = acc[j] + bia[blk];
+                        for (int j = 0; j < 16; ++j) {             // GDN backward (gdn_math.cuh gdn_bwd1<false>) with the one-MUFU rsqrt;
+                            const float v = acc[j] + bia[blk];     // the constant factors (-1/2, beta) of the three sums are applied once, at the end
                             const float x2 = v * v;
                             const float r = rsqrt_fast(fmaf(gamma[blk], x2, beta[blk]));
-                            const float gr3 = gq[j] * (r * r * r);  // gq = 0 past the end: no contribution
-                            const float dv = gr3 * beta[blk], hb = -0.5f * gr3 * v;
-                            sum_b[blk] += hb;
-                            sum_g[blk] = fmaf(hb, x2, sum_g[blk]);
-                            sum_v[blk] += dv;
+                            const float gr3 = gq[j] * (r * r * r);  // g / d^3; gq = 0 past the end: no contribution
+                            const float t = gr3 * v;
+                            sum_b[blk] += t;                        // d(beta)  = -1/2 sum g v / d^3
+                            sum_g[blk] = fmaf(t, x2, sum_g[blk]);   // d(gamma) = -1/2 sum g v^3 / d^3
+                            sum_v[blk] += gr3;                      // d(bias)  = beta sum g / d^3
+                            const float dv = gr3 * beta[blk];
                             acc[j] = tf32_hi(dv);
                             lo[j] = dv - acc[j];
                         }
@@ -297,7 +298,7 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
 #pragma unroll
             for (int blk = 0; blk < MB; ++blk) {
                 float *r = red + ((cg * MB + blk) * 128 + q * 32 + lane) * 3;
-                r[0] = sum_b[blk]; r[1] = sum_g[blk]; r[2] = sum_v[blk];
+                r[0] = -0.5f * sum_b[blk]; r[1] = -0.5f * sum_g[blk]; r[2] = beta[blk] * sum_v[blk];
             }
         }
     } else if (warp < kC0Epi + kC0Prod) {
@@ -329,10 +330,20 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
                 }
             }
         };
+        auto prefetch_g = [&](long t) {   // backward: DRAM latency of the epilogue's grad_y reads is taken tiles ahead by one bulk L2 prefetch
+            if (BWD && pp == 0 && t < n_tiles) {
+                const long rows = (g.P - t * TN < TN) ? (g.P - t * TN) : TN;
+                prefetch_l2_bulk(gy + (size_t)t * TN * C, (uint32_t)(rows * C * 4));
+            }
+        };
         request(blockIdx.x);
+        prefetch_g(blockIdx.x);
+        prefetch_g(blockIdx.x + (long)gridDim.x);
+        prefetch_g(blockIdx.x + 2 * (long)gridDim.x);
         uint32_t u = 0;
         for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++u) {
             const uint32_t s1 = u % NS1, ph1 = (u / NS1) & 1;
+            prefetch_g(tile + 3 * (long)gridDim.x);
             const uint32_t sPh = sStage1 + s1 * 2 * Cfg::P_BYTES, sPl = sPh + Cfg::P_BYTES;
             mbar_wait(bar_empty1 + 8 * s1, ph1 ^ 1);
             if (active) {

@@ -406,6 +406,60 @@ def conv0_gdn(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# N2, synthesis side: the last layer ConvTranspose2d(N, 3, 5, 2, 2, output_padding=1) as GEMM + gather
+class _Col2ImRGB(torch.autograd.Function):
+    """The scatter half of layers.py:96-98 (`deconv(N, 3)`) as a deterministic gather (csrc/deconv_rgb.cu): D [B,80,H,W] channels-last
+    (75 tap columns (kh, kw, co) + 5 zero columns per position) -> x_hat [B,3,2H,2W] channels-last; backward = the adjoint gather."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, D, bias):
+        lib = _lib.load()
+        if D.dim() != 4 or D.shape[1] != 80:
+            raise _lib.SicError("col2im_rgb expects D [B,80,H,W]")
+        Dc = _dense_layout(D.contiguous(memory_format=torch.channels_last), "D")[0]
+        bias = None if bias is None else _require_cuda_f32(bias, "bias")
+        B, _, H, W = Dc.shape
+        out = torch.empty((B, 3, 2 * H, 2 * W), dtype=torch.float32, device=D.device, memory_format=torch.channels_last)
+        with torch.cuda.device(D.device):
+            _launch(lib.sic_deconv_rgb_col2im(_ptr(Dc), _ptr(bias), B, H, W, _ptr(out), _stream()), "sic_deconv_rgb_col2im")
+        ctx.geom = (B, H, W, bias is not None)
+        return out
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g):
+        lib = _lib.load()
+        B, H, W, has_bias = ctx.geom
+        g = _dense_layout(g.contiguous(memory_format=torch.channels_last), "grad_output")[0]
+        dD = None
+        if ctx.needs_input_grad[0]:
+            dD = torch.empty((B, 80, H, W), dtype=torch.float32, device=g.device, memory_format=torch.channels_last)
+            with torch.cuda.device(g.device):
+                _launch(lib.sic_deconv_rgb_im2col(_ptr(g), B, H, W, _ptr(dD), _stream()), "sic_deconv_rgb_im2col")
+        dbias = g.sum(dim=(0, 2, 3)) if (has_bias and ctx.needs_input_grad[1]) else None
+        return dD, dbias
+
+
+def deconv_rgb(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """conv_transpose2d(a, weight [N,3,5,5], bias, stride 2, padding 2, output_padding 1) as  D = 1x1 convolution N -> 75 (+5 zero
+    columns; cuDNN's sm_100 tensor-op kernels, forward / dgrad / wgrad through autograd)  followed by the deterministic col2im
+    gather; returns a channels_last [B,3,2H,2W] tensor.  cuDNN runs the 3-band transposed convolution itself on legacy
+    non-tensor-core engines (238 us forward, 438 us backward per cfg2 step).  Same precision policy as the layer it replaces
+    (torch.backends.cudnn.allow_tf32 governs both).  Opt-in training path (layers.FAST_LAST_LAYER); eval/compress keep the
+    cuDNN layer, whose x_hat is pinned bit for bit."""
+    if not (isinstance(a, torch.Tensor) and a.is_cuda):
+        raise _lib.SicError("deconv_rgb: expected a CUDA tensor — this package has no CPU path (the CPU oracle is oracle/, test only)")
+    N = a.shape[1]
+    if a.dim() != 4 or tuple(weight.shape) != (N, 3, 5, 5):
+        raise _lib.SicError(f"deconv_rgb: weight {tuple(weight.shape)} is not [{N},3,5,5] for activations {tuple(a.shape)}")
+    wm = weight.permute(2, 3, 1, 0).reshape(75, N)                              # row m = (kh, kw, co)
+    wm = torch.nn.functional.pad(wm, (0, 0, 0, 5)).view(80, N, 1, 1)
+    D = torch.nn.functional.conv2d(a.contiguous(memory_format=torch.channels_last), wm)
+    return _Col2ImRGB.apply(D, bias)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # N4: tail of the hyper-synthesis transform
 class _HyperTail(torch.autograd.Function):
     @staticmethod

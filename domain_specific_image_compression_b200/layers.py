@@ -53,6 +53,17 @@ def _first_layer_fusable(m, nxt, x, training):
             and x.is_cuda and x.dtype == torch.float32 and not x.requires_grad and PAD_RGB_CHANNELS <= 3)
 
 
+# Opt-in like FUSE_FIRST_LAYER, same reasons: in TRAINING mode the last synthesis layer deconv(N, 3) runs as GEMM + gather
+# (F_sic.deconv_rgb) instead of cuDNN's legacy 3-band engines.
+FAST_LAST_LAYER = False
+
+
+def _last_layer_fast(m, x, training):
+    return (FAST_LAST_LAYER and training and isinstance(m, nn.ConvTranspose2d) and m.out_channels == 3 and m.kernel_size == (5, 5)
+            and m.stride == (2, 2) and m.padding == (2, 2) and m.output_padding == (1, 1) and m.dilation == (1, 1) and m.groups == 1
+            and x.is_cuda and PAD_RGB_CHANNELS <= 3)
+
+
 PAD_RGB_CHANNELS = 0       # 4 or 8: run the 3-channel first conv / last transposed conv with zero-padded channels (see _rgb_padded)
 
 
@@ -94,6 +105,10 @@ def _run(seq: nn.Sequential, x):
         if _first_layer_fusable(m, nxt, x, seq.training):
             x = F_sic.conv0_gdn(x, m.weight, m.bias, nxt.beta, nxt.gamma_conv.weight)
             i += 2
+            continue
+        if _last_layer_fast(m, x, seq.training):
+            x = F_sic.deconv_rgb(x, m.weight, m.bias)
+            i += 1
             continue
         padded = _rgb_padded(m, x) if (PAD_RGB_CHANNELS > 3 and x.is_cuda) else None
         if padded is not None:

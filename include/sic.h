@@ -163,6 +163,16 @@ int sic_conv0_gdn_bwd(const float *x, const float *w, const float *bias, const f
                       const float *grad_y, int B, int H, int W, int C, float *dw, float *dbias, float *dbeta_param,
                       float *dgamma_weight, void *workspace, size_t workspace_bytes, void *stream);
 
+/* N2, synthesis side: the gather halves of the last layer ConvTranspose2d(N, 3, 5, stride 2, padding 2, output_padding 1)
+ * (layers.py:96-98) in its GEMM formulation (csrc/deconv_rgb.cu); the GEMM itself (a 1x1 convolution N -> 80) is a library call.
+ *   D [P, 80] position-major (the channels-last output of the 1x1 convolution), P = B*H*W over the INPUT grid, column
+ *   m = (kh * 5 + kw) * 3 + co for m < 75, columns 75..79 ignored (read) / zero (written).
+ *   col2im: out [B, 2H, 2W, 3] channels-last = bias + sum of the taps that land on each output pixel, gathered in a fixed order
+ *           (no atomics: deterministic; every tap element of D is read exactly once).  bias nullable.
+ *   im2col: dD[p, m] = grad_out[b, 2 iy - 2 + kh, 2 ix - 2 + kw, co] (0 outside the image): the adjoint gather. */
+int sic_deconv_rgb_col2im(const float *D, const float *bias, int B, int H, int W, float *out, void *stream);
+int sic_deconv_rgb_im2col(const float *grad_out, int B, int H, int W, float *dD, void *stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * N4  tail of the hyper-synthesis transform in one launch: layers.py:141-152 (AdaptiveAvgPool2d(1) -> mlp_sigma / mlp_nu, two 1x1
  * convolutions with a ReLU each) + model.py:54-55 (exp, mean over an already constant map, clamp of nu); the decoder runs the same

@@ -25,27 +25,22 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def time_it(fn, reps=args.reps, nbytes=0):
     """Kernels that stream >= 256 MB (2 x the 126 MB L2, walked front to back) are timed without a flush: "inputs larger than L2"
     (B200_PROFILING.md).  Flushing by writing 256 MB leaves 126 MB of dirty lines whose write-back is billed to the kernel.  Those
-    launches are captured `reps` times into one CUDA graph and the replay is timed (launch gaps as inside the step's own graph,
-    not Python's dispatch time); --eager-timing keeps the per-launch event pairs."""
+    launches are queued `reps` at a time behind a ~1 ms device-side spin (the host is then a full queue ahead: launch gaps are the
+    device's own, as inside the step's CUDA graph); one event pair per batch, time / reps, median of 3.  --eager-timing keeps
+    per-launch event pairs."""
     for _ in range(3): fn()
     big = nbytes >= (256 << 20)
     if big and not args.eager_timing:
-        try:
-            torch.cuda.synchronize()
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
-                for _ in range(reps): fn()
-            gr.replay(); ts = []
-            for _ in range(5):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); gr.replay(); e1.record(); torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1) / reps)
-            del gr
-            ts.sort()
-            return ts[len(ts) // 2] * 1e-3
-        except Exception as e:
-            print(f"graph timing unavailable ({type(e).__name__}: {str(e)[:100]}); eager", flush=True)
-            torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            torch.cuda._sleep(2_000_000)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps): fn()
+            e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / reps)
+        ts.sort()
+        return ts[1] * 1e-3
     ts = []
     for _ in range(reps):
         if not big: flush.zero_()
@@ -167,5 +162,29 @@ if args.only in ("", "conv0"):
             del y, go, x
         except Exception as e:
             print(f"conv0 {B}x{C}: FAILED {type(e).__name__}: {e}", flush=True)
+if args.only in ("", "deconv"):
+    # N2, synthesis side: last layer deconv(N, 3) as library GEMM + gather kernels vs cuDNN's conv_transpose2d (legacy 3-band engines).
+    # Algorithmic bytes: forward = a in + x_hat out; backward = a, grad in + d(a) out.
+    import torch.nn.functional as TF
+    torch.backends.cudnn.benchmark = True
+    for (B, N, H, W) in [(16, 128, 128, 128), (8, 192, 128, 128)]:
+        try:
+            a = torch.randn(B, N, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+            w = torch.randn(N, 3, 5, 5, device=dev) * 0.1
+            bias = torch.randn(3, device=dev)
+            n, no = a.numel(), B * 3 * 4 * H * W
+            fb, bb = 4 * (n + no), 4 * (2 * n + no)
+            report("deconv_rgb GEMM+col2im fwd", (B, N, H, W), fb, time_it(lambda: F.deconv_rgb(a, w, bias), nbytes=1 << 30))
+            ps = [t.clone().requires_grad_(True) for t in (a, w, bias)]
+            y = F.deconv_rgb(*ps); go = torch.randn_like(y)
+            report("deconv_rgb im2col+2 GEMM bwd", (B, N, H, W), bb, time_it(lambda: torch.autograd.grad(y, ps, go, retain_graph=True), nbytes=1 << 30))
+            del y
+            report("deconv cuDNN fwd", (B, N, H, W), fb, time_it(lambda: TF.conv_transpose2d(a, w, bias, 2, 2, 1), nbytes=1 << 30))
+            ps = [t.clone().requires_grad_(True) for t in (a, w, bias)]
+            y = TF.conv_transpose2d(*ps, 2, 2, 1)
+            report("deconv cuDNN bwd", (B, N, H, W), bb, time_it(lambda: torch.autograd.grad(y, ps, go, retain_graph=True), nbytes=1 << 30))
+            del y, go, a
+        except Exception as e:
+            print(f"deconv {B}x{N}: FAILED {type(e).__name__}: {e}", flush=True)
 if args.json:
     json.dump({"peak_gbs": PEAK, "rows": rows}, open(args.json, "w"), indent=1)

@@ -75,3 +75,21 @@ if which_set & {"ssim"}:
         losses.multi_scale_ssim(a, b, 1.0, torch.tensor([0.3, 0.5, 0.2], device=dev)).backward()
 torch.cuda.synchronize()
 print("ok")
+if which_set & {"conv0"}:
+    x = torch.rand(16, 3, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(128, 3, 3, 3, device=dev) * 0.3).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(128, device=dev) * 0.2
+    beta = torch.sqrt(torch.rand(128, device=dev) + 0.5); gw = torch.sqrt(torch.rand(128, 1, 1, 1, device=dev) * 0.3 + 0.01)
+    ps = [t.clone().requires_grad_(True) for t in (w, bias, beta, gw)]
+    for _ in range(reps):
+        yv = F.conv0_gdn(x, *ps)
+        torch.autograd.grad(yv, ps, torch.randn_like(yv))
+    del x, yv
+if which_set & {"deconv"}:
+    a = torch.randn(16, 128, 128, 128, device=dev).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = (torch.randn(128, 3, 5, 5, device=dev) * 0.1).requires_grad_(True)
+    bias = torch.randn(3, device=dev).requires_grad_(True)
+    for _ in range(reps):
+        yv = F.deconv_rgb(a, w, bias)
+        torch.autograd.grad(yv, (a, w, bias), torch.randn_like(yv))
+    del a, yv

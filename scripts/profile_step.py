@@ -28,7 +28,7 @@ def prof(fn, tag):
         for _ in range(3): fn()
         torch.cuda.synchronize()
     print(f"==== {tag}: top kernels over 3 steps")
-    print(p.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+    print(p.key_averages().table(sort_by="cuda_time_total", row_limit=int(os.environ.get("ROWS", "45")), max_name_column_width=70))
 
 if which in ("both", "ours"):
     torch.manual_seed(42)
@@ -37,6 +37,10 @@ if which in ("both", "ours"):
         model.g_a.g_a[14].weight.mul_(40.0); model.h_a.h_a[6].weight.mul_(40.0); model.h_s.mlp_nu[2].bias.add_(1.5)
     if os.environ.get("CHANNELS_LAST"):
         model = model.to(memory_format=torch.channels_last); x = x.contiguous(memory_format=torch.channels_last)
+    from domain_specific_image_compression_b200 import layers as _L
+    _L.FUSE_FIRST_LAYER = bool(os.environ.get("FUSE_FIRST", "1") != "0" and os.environ.get("CHANNELS_LAST"))
+    _L.FAST_LAST_LAYER = bool(os.environ.get("FAST_LAST", "1") != "0" and os.environ.get("CHANNELS_LAST"))
+    print("fused first layer", _L.FUSE_FIRST_LAYER, "gemm last layer", _L.FAST_LAST_LAYER)
     tr = FlatTrainer(model)
     def closure():
         out = model(x, "noise"); return sic.rate_distortion_loss(out, x, 10000.0, "msssim")[0]
