@@ -233,7 +233,8 @@ def run_ours(args):
     cfg = CONFIGS[args.config]
     B, H, W = cfg["batch"], cfg["H"], cfg["W"]
     # kernel rooflines first: they draw from torch's CUDA generator, which must not be touched between graph replays
-    roof, kernels = kernel_rooflines(cfg, dev, channels_last=not args.nchw) if rank == 0 else (None, None)
+    fused_first = not (args.no_fuse_first_layer or args.pad_rgb or args.gdn == "dense" or args.nchw)
+    roof, kernels = kernel_rooflines(cfg, dev, channels_last=not args.nchw, fused_first_layer=fused_first) if rank == 0 else (None, None)
     torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     gpu_eager = None
     if rank == 0 and world == 1 and not args.no_gpu_eager_baseline:
@@ -399,7 +400,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def kernel_rooflines(cfg, dev, channels_last=True):
+def kernel_rooflines(cfg, dev, channels_last=True, fused_first_layer=True):
     """CUDA-event timing of our own kernels at the sizes they have inside the step (largest GDN site, the latent), inputs
     larger than L2 or L2 flushed in between.  achieved = algorithmic bytes / time (GDN fwd 8 B/elem,
     bwd 12 B/elem; K1 fwd 12 B/elem broadcast, bwd 8 B/elem + 4 for the dense upstream of y_tilde)."""
@@ -472,6 +473,35 @@ def kernel_rooflines(cfg, dev, channels_last=True):
     t = time_it(lambda: torch.autograd.grad(yc, (xcr, beta, w), gc, retain_graph=True), big=True)
     out["gdn_bwd_channels_last"] = {"shape": list(x.shape), "bytes": 12 * n, "ms": t * 1e3, "gbs": 12 * n / t / 1e9}
     del x, g, xr, y, xc, gc, xcr, yc
+    # the 128^2 sites (two GDN + two IGDN per step): the largest GDN/IGDN sites of the step once the first layer is fused
+    x = torch.randn(B, N, 128, 128, device=dev).contiguous(memory_format=torch.channels_last)
+    g = torch.randn_like(x)
+    n = x.numel()
+    t = time_it(lambda: F.gdn(x, beta, w, False), big=8 * n >= (256 << 20))
+    out["gdn_fwd_channels_last_128"] = {"shape": list(x.shape), "bytes": 8 * n, "ms": t * 1e3, "gbs": 8 * n / t / 1e9}
+    xr = x.clone().requires_grad_(True)
+    y = F.gdn(xr, beta, w, False)
+    t = time_it(lambda: torch.autograd.grad(y, (xr, beta, w), g, retain_graph=True), big=12 * n >= (256 << 20))
+    out["gdn_bwd_channels_last_128"] = {"shape": list(x.shape), "bytes": 12 * n, "ms": t * 1e3, "gbs": 12 * n / t / 1e9}
+    del x, g, xr, y
+    # N2: the fused first analysis layer (image in, y out / grad_y in): algorithmic bytes = the activation tensor once + the image
+    try:
+        img = torch.rand(B, 3, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
+        w0 = (torch.randn(N, 3, 3, 3, device=dev) * 0.3).contiguous(memory_format=torch.channels_last)
+        b0 = torch.randn(N, device=dev) * 0.2
+        n = B * N * 256 * 256
+        nb = 4 * (n + img.numel())
+        t = time_it(lambda: F.conv0_gdn(img, w0, b0, beta, w), big=True)
+        out["conv0_gdn_fwd_tcgen05"] = {"shape": [B, N, 256, 256], "bytes": nb, "ms": t * 1e3, "gbs": nb / t / 1e9}
+        ps = [v.detach().clone().requires_grad_(True) for v in (w0, b0, beta, w)]
+        y = F.conv0_gdn(img, *ps)
+        g = torch.randn_like(y)
+        t = time_it(lambda: torch.autograd.grad(y, ps, g, retain_graph=True), big=True)
+        out["conv0_gdn_bwd_tcgen05"] = {"shape": [B, N, 256, 256], "bytes": nb, "ms": t * 1e3, "gbs": nb / t / 1e9,
+                                        "note": "both launches of the backward (main kernel + fold of the per-CTA partials)"}
+        del img, y, g
+    except Exception as e:
+        out["conv0_gdn_fwd_tcgen05"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
     # likelihood kernel: the step's latent is tiny (launch-latency bound); the roofline figure is quoted on the top of the
     # BASELINE cfg5 sweep (128x128x320 latent, batch 16 = 84M elements, 1 GB of traffic)
     for tag, shape in (("k1_fwd_step", (B, M, 16, 16)), ("k1_fwd_sweep_top", (16, 320, 128, 128))):
@@ -526,12 +556,18 @@ def kernel_rooflines(cfg, dev, channels_last=True):
                                                "note": "dx, d(beta), d(gamma): all launches of the backward"}
         del xd, xr, yv, go
     for v in out.values():
-        v["frac_of_hbm_peak"] = v["gbs"] / peak
+        if "gbs" in v:
+            v["frac_of_hbm_peak"] = v["gbs"] / peak
     # The dominant own kernel of the step is the GDN backward at the largest site, in the layout the step actually runs
     # (channels_last by default -> gdn_bwd_nhwc_kernel; --nchw -> gdn_bwd_kernel).  `traffic` = dram__bytes_read.sum +
     # dram__bytes_write.sum of that kernel at this shape, looked up in profiles/ncu_traffic.json (written by scripts/ncu_traffic.py
     # from a committed ncu --set full capture) and used ONLY if the capture's registers/thread equal those of the loaded library.
-    if channels_last:
+    if channels_last and fused_first_layer:
+        dom, kid = out["gdn_bwd_channels_last_128"], "gdn_bwd_nhwc_kernel<0>"
+        kname = ("gdn_bwd_nhwc_kernel (GDN/IGDN backward, channels_last; 12 launches and the largest share of the step among our kernels: "
+                 "profiles/r02h_ncu_launches_bench_step.txt) at its largest site in the step, 128^2 (the 256^2 site is inside the fused "
+                 "first-layer kernel; this kernel at 256^2: kernels.gdn_bwd_channels_last)")
+    elif channels_last:
         dom, kid = out["gdn_bwd_channels_last"], "gdn_bwd_nhwc_kernel<0>"
         kname = "gdn_bwd_nhwc_kernel (GDN backward, channels_last) at the largest site of the step"
     else:
@@ -546,8 +582,9 @@ def kernel_rooflines(cfg, dev, channels_last=True):
     roof = {"kernel": kname, "bound": "hbm", "achieved": dom["gbs"], "peak": peak,
             "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic, "traffic_source": tsrc, "registers_per_thread": regs,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"],
-            "timing": "CUDA events on the launching stream around the whole backward of the site (main kernel + the per-channel "
-                      "finalize); 10 back-to-back repetitions of a 1.6 GB working set (13 x the L2: no flush needed, none done), a queued spin lets the host run ahead; median"}
+            "timing": "CUDA events on the launching stream around 10 back-to-back backward passes of the site (each = main kernel + the "
+                      "per-channel finalize launch), queued behind a 1 ms device-side spin so the host is a full queue ahead; working set "
+                      ">= 3 x the 126 MB L2, walked front to back: no flush needed, none done; time / 10, median of 3 batches"}
     return roof, out
 
 

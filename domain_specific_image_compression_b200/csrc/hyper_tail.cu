@@ -23,19 +23,30 @@
 namespace sic {
 namespace {
 
-constexpr int kHtThreads = 256, kHtWarps = kHtThreads / 32;
+constexpr int kHtThreads = 1024, kHtWarps = kHtThreads / 32;   // one CTA per patch: the chain is latency-bound, so it gets a full SM's warps
 
 struct Mlp {
     const float *w1, *b1, *w2, *b2;   // [N,N], [N], [M,N], [M]
 };
 
-__device__ __forceinline__ float dot_row(const float *__restrict__ w, const float *v, int n, int lane) {
-    float a = 0.f;
-    for (int c = lane; c < n; c += 32) a = fmaf(__ldg(w + c), v[c], a);
-    return warp_sum(a);
+// Two rows at a time (independent loads in flight for both), each in the order `lane l sums c = l, l+32, ... then a warp tree`.
+__device__ __forceinline__ void dot_rows2(const float *__restrict__ w0, const float *__restrict__ w1, const float *v, int n, int lane, float &r0,
+                                          float &r1) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+    for (int c = lane; c < n; c += 32) {
+        const float x = v[c];
+        a0 = fmaf(__ldg(w0 + c), x, a0);
+        a1 = fmaf(__ldg(w1 + c), x, a1);
+    }
+    r0 = warp_sum(a0);
+    r1 = warp_sum(a1);
 }
 
 // save layout per patch: p[N], hid_sigma[N], hid_nu[N], e_nu[M] (= exp(log_nu) before the clamp)
+// r02i: 100 us per launch with 8 warps per patch (16 channels pooled one after the other per warp through lane-strided,
+// 512-byte-apart loads; 32 / 48 dependent row dots per warp).  Now 32 warps, channels-last pooling four channels per 128-bit load with
+// all loads of a lane independent, two rows per dot: same sums in the same order, a few microseconds.
 __global__ void __launch_bounds__(kHtThreads) hyper_tail_fwd_kernel(const float *__restrict__ t, int N, int M, int HW, int channels_last,
                                                                   Mlp ms, Mlp mn, float min_nu, float max_nu, float *__restrict__ sigma,
                                                                   float *__restrict__ nu, float *__restrict__ save) {
@@ -43,35 +54,73 @@ __global__ void __launch_bounds__(kHtThreads) hyper_tail_fwd_kernel(const float 
     float *p = sm, *hs = sm + N, *hn = sm + 2 * N;
     const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float *tb = t + (size_t)b * N * HW;
-    for (int c = warp; c < N; c += kHtWarps) {
-        float a = 0.f;
-        if (channels_last) for (int s = lane; s < HW; s += 32) a += __ldg(tb + (size_t)s * N + c);
-        else for (int s = lane; s < HW; s += 32) a += __ldg(tb + (size_t)c * HW + s);
-        a = warp_sum(a);
-        if (lane == 0) p[c] = __fdiv_rn(a, (float)HW);
+    if (channels_last && (N & 3) == 0 && ((uintptr_t)tb & 15) == 0) {
+        for (int q = warp; q < N / 4; q += kHtWarps) {           // lane l sums positions l, l+32, ... of four channels at once
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+            for (int sidx = lane; sidx < HW; sidx += 32) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(tb + (size_t)sidx * N) + q);
+                a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            }
+            a.x = warp_sum(a.x); a.y = warp_sum(a.y); a.z = warp_sum(a.z); a.w = warp_sum(a.w);
+            if (lane == 0) {
+                p[4 * q] = __fdiv_rn(a.x, (float)HW); p[4 * q + 1] = __fdiv_rn(a.y, (float)HW);
+                p[4 * q + 2] = __fdiv_rn(a.z, (float)HW); p[4 * q + 3] = __fdiv_rn(a.w, (float)HW);
+            }
+        }
+    } else {
+        for (int c = warp; c < N; c += kHtWarps) {
+            float a = 0.f;
+            if (channels_last) {
+#pragma unroll 8
+                for (int sidx = lane; sidx < HW; sidx += 32) a += __ldg(tb + (size_t)sidx * N + c);
+            } else {
+#pragma unroll 8
+                for (int sidx = lane; sidx < HW; sidx += 32) a += __ldg(tb + (size_t)c * HW + sidx);
+            }
+            a = warp_sum(a);
+            if (lane == 0) p[c] = __fdiv_rn(a, (float)HW);
+        }
     }
     __syncthreads();
-    for (int j = warp; j < 2 * N; j += kHtWarps) {
-        const bool second = j >= N;
-        const int r = second ? j - N : j;
-        const Mlp &m = second ? mn : ms;
-        float a = dot_row(m.w1 + (size_t)r * N, p, N, lane) + __ldg(m.b1 + r);
-        if (lane == 0) (second ? hn : hs)[r] = fmaxf(a, 0.f);
+    for (int j = warp; j < N; j += kHtWarps) {                   // row j of both first layers
+        float a0, a1;
+        dot_rows2(ms.w1 + (size_t)j * N, mn.w1 + (size_t)j * N, p, N, lane, a0, a1);
+        if (lane == 0) {
+            hs[j] = fmaxf(a0 + __ldg(ms.b1 + j), 0.f);
+            hn[j] = fmaxf(a1 + __ldg(mn.b1 + j), 0.f);
+        }
     }
     __syncthreads();
     float *sv = save ? save + (size_t)b * (3 * N + M) : nullptr;
-    for (int j = warp; j < 2 * M; j += kHtWarps) {
-        const bool second = j >= M;
-        const int r = second ? j - M : j;
-        const Mlp &m = second ? mn : ms;
-        float a = dot_row(m.w2 + (size_t)r * N, second ? hn : hs, N, lane) + __ldg(m.b2 + r);
+    for (int j = warp; j < 2 * M; j += 2 * kHtWarps) {           // rows j and j + kHtWarps of the stacked second layers
+        const int j1 = j + kHtWarps;
+        const bool sec0 = j >= M, sec1 = j1 >= M;
+        const int r0 = sec0 ? j - M : j, r1 = (j1 < 2 * M) ? (sec1 ? j1 - M : j1) : r0;
+        const Mlp &m0 = sec0 ? mn : ms, &m1 = sec1 ? mn : ms;
+        float a0 = 0.f, a1 = 0.f;
+        {   // the two rows may read different hidden vectors: two accumulation chains, each in the fixed order
+#pragma unroll 4
+            for (int c = lane; c < N; c += 32) {
+                a0 = fmaf(__ldg(m0.w2 + (size_t)r0 * N + c), (sec0 ? hn : hs)[c], a0);
+                a1 = fmaf(__ldg(m1.w2 + (size_t)r1 * N + c), (sec1 ? hn : hs)[c], a1);
+            }
+            a0 = warp_sum(a0);
+            a1 = warp_sum(a1);
+        }
         if (lane == 0) {
-            const float e = expf(a);
-            if (second) {
-                nu[(size_t)b * M + r] = fminf(fmaxf(e, min_nu), max_nu);
-                if (sv) sv[3 * N + r] = e;
-            } else {
-                sigma[(size_t)b * M + r] = e;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k == 1 && j1 >= 2 * M) break;
+                const bool second = k ? sec1 : sec0;
+                const int r = k ? r1 : r0;
+                const float e = expf((k ? a1 : a0) + __ldg((second ? mn : ms).b2 + r));
+                if (second) {
+                    nu[(size_t)b * M + r] = fminf(fmaxf(e, min_nu), max_nu);
+                    if (sv) sv[3 * N + r] = e;
+                } else {
+                    sigma[(size_t)b * M + r] = e;
+                }
             }
         }
     }
@@ -79,16 +128,20 @@ __global__ void __launch_bounds__(kHtThreads) hyper_tail_fwd_kernel(const float 
 }
 
 // scratch layout per patch: dlog_sigma[M], dlog_nu[M], dhid_sigma[N], dhid_nu[N]
+// The two matrix-vector products of the chain (W2^T dlog: 2N outputs of length M; W1^T dhid: N outputs of length 2N) are split over
+// the CTA's 1024 threads as (output, chunk of the reduction axis): every thread runs a short, 8-way unrolled chain of independent
+// loads, the chunk partials meet in shared memory and are added in chunk order (fixed order: deterministic).  r02i: 57 us per
+// launch with one thread per output walking the whole axis.
 __global__ void __launch_bounds__(kHtThreads) hyper_tail_bwd_kernel(const float *__restrict__ dsigma, const float *__restrict__ dnu,
                                                                   const float *__restrict__ sigma, const float *__restrict__ save, int N, int M,
                                                                   int HW, int channels_last, Mlp ms, Mlp mn, float min_nu, float max_nu,
                                                                   float *__restrict__ dt, float *__restrict__ scratch) {
-    extern __shared__ float sm[];   // dls[M], dln[M], dhs[N], dhn[N], dp[N]
-    float *dls = sm, *dln = sm + M, *dhs = sm + 2 * M, *dhn = dhs + N, *dp = dhn + N;
-    const int b = blockIdx.x;
+    extern __shared__ float sm[];   // dls[M], dln[M], dhs[N], dhn[N], dp[N], red[kHtThreads]
+    float *dls = sm, *dln = sm + M, *dhs = sm + 2 * M, *dhn = dhs + N, *dp = dhn + N, *red = dp + N;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const float *sv = save + (size_t)b * (3 * N + M);
     float *sc = scratch + (size_t)b * (2 * M + 2 * N);
-    for (int m = threadIdx.x; m < M; m += kHtThreads) {
+    for (int m = tid; m < M; m += kHtThreads) {
         const float gs = dsigma ? dsigma[(size_t)b * M + m] : 0.f, gn = dnu ? dnu[(size_t)b * M + m] : 0.f;
         const float e = sv[3 * N + m];
         const float a = gs * sigma[(size_t)b * M + m];                         // d/dlog_sigma of exp
@@ -97,31 +150,64 @@ __global__ void __launch_bounds__(kHtThreads) hyper_tail_bwd_kernel(const float 
         sc[m] = a; sc[M + m] = c;
     }
     __syncthreads();
-    for (int n = threadIdx.x; n < 2 * N; n += kHtThreads) {                    // dhid[n] = relu'(hid[n]) * sum_m W2[m,n] dlog[m]
-        const bool second = n >= N;
-        const int r = second ? n - N : n;
-        const float *w2 = (second ? mn : ms).w2;
-        const float *dl = second ? dln : dls;
+    // dhid[n] = relu'(hid[n]) * sum_m W2[m,n] dlog[m]        (n over both MLPs: 2N outputs)
+    for (int base = 0; base < 2 * N; base += kHtThreads) {
+        const int n_out = min(2 * N - base, kHtThreads);
+        const int chunks = kHtThreads / n_out, len = (M + chunks - 1) / chunks;
+        const int chunk = tid / n_out, o = tid - chunk * n_out, n = base + o;
         float a = 0.f;
-        for (int m = 0; m < M; ++m) a = fmaf(__ldg(w2 + (size_t)m * N + r), dl[m], a);
-        a = sv[(second ? 2 * N : N) + r] > 0.f ? a : 0.f;
-        (second ? dhn : dhs)[r] = a;
-        sc[2 * M + n] = a;
+        if (chunk < chunks) {
+            const bool second = n >= N;
+            const int r = second ? n - N : n;
+            const float *w2 = (second ? mn : ms).w2 + r;
+            const float *dl = second ? dln : dls;
+            const int m1 = min(M, (chunk + 1) * len);
+#pragma unroll 8
+            for (int m = chunk * len; m < m1; ++m) a = fmaf(__ldg(w2 + (size_t)m * N), dl[m], a);
+        }
+        red[tid] = a;
+        __syncthreads();
+        if (tid < n_out) {
+            float t = 0.f;
+            for (int k = 0; k < chunks; ++k) t += red[k * n_out + tid];
+            const bool second = n >= N;
+            const int r = second ? n - N : n;
+            t = sv[(second ? 2 * N : N) + r] > 0.f ? t : 0.f;
+            (second ? dhn : dhs)[r] = t;
+            sc[2 * M + n] = t;
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    // dp[c] = (sum_j W1s[j,c] dhs[j] + W1n[j,c] dhn[j]) / (h w)    (reduction axis: the stacked 2N hidden units)
     const float inv = 1.0f / (float)HW;
-    for (int c = threadIdx.x; c < N; c += kHtThreads) {                        // dp[c] = sum_j W1s[j,c] dhs[j] + W1n[j,c] dhn[j]
+    for (int base = 0; base < N; base += kHtThreads) {
+        const int n_out = min(N - base, kHtThreads);
+        const int chunks = kHtThreads / n_out, len = (2 * N + chunks - 1) / chunks;
+        const int chunk = tid / n_out, o = tid - chunk * n_out, c = base + o;
         float a = 0.f;
-        for (int j = 0; j < N; ++j) a = fmaf(__ldg(ms.w1 + (size_t)j * N + c), dhs[j], a);
-        for (int j = 0; j < N; ++j) a = fmaf(__ldg(mn.w1 + (size_t)j * N + c), dhn[j], a);
-        dp[c] = a * inv;
+        if (chunk < chunks) {
+            const int j1 = min(2 * N, (chunk + 1) * len);
+#pragma unroll 8
+            for (int j = chunk * len; j < j1; ++j) {
+                const bool second = j >= N;
+                const int r = second ? j - N : j;
+                a = fmaf(__ldg((second ? mn : ms).w1 + (size_t)r * N + c), (second ? dhn : dhs)[r], a);
+            }
+        }
+        red[tid] = a;
+        __syncthreads();
+        if (tid < n_out) {
+            float t = 0.f;
+            for (int k = 0; k < chunks; ++k) t += red[k * n_out + tid];
+            dp[c] = t * inv;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (dt) {
         float *db = dt + (size_t)b * N * HW;
         const long n = (long)N * HW;
-        if (channels_last) for (long i = threadIdx.x; i < n; i += kHtThreads) db[i] = dp[i % N];
-        else for (long i = threadIdx.x; i < n; i += kHtThreads) db[i] = dp[i / HW];
+        if (channels_last) for (long i = tid; i < n; i += kHtThreads) db[i] = dp[i % N];
+        else for (long i = tid; i < n; i += kHtThreads) db[i] = dp[i / HW];
     }
 }
 
@@ -191,7 +277,7 @@ extern "C" int sic_hyper_tail_bwd(const float *dsigma, const float *dnu, const f
     SIC_CHECK_ARG(N <= 2048 && M <= 4096, "sic_hyper_tail_bwd: N=%d / M=%d exceed the shared-memory staging", N, M);
     cudaStream_t st = (cudaStream_t)stream;
     Mlp ms{w1s, nullptr, w2s, nullptr}, mn{w1n, nullptr, w2n, nullptr};
-    hyper_tail_bwd_kernel<<<B, kHtThreads, (2 * M + 3 * N) * sizeof(float), st>>>(dsigma, dnu, sigma, save, N, M, HW, channels_last, ms, mn,
+    hyper_tail_bwd_kernel<<<B, kHtThreads, (2 * M + 3 * N + kHtThreads) * sizeof(float), st>>>(dsigma, dnu, sigma, save, N, M, HW, channels_last, ms, mn,
                                                                                  min_nu, max_nu, dt, scratch);
     SIC_CHECK_LAUNCH("sic_hyper_tail_bwd");
     const int total = 2 * (N * N + N + M * N + M);

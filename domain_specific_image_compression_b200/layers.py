@@ -39,7 +39,7 @@ class GDN(nn.Module):
 FUSE_CONV_BIAS = True      # fold each convolution's bias add (and its gradient reduction) into the following GDN kernel
 
 
-# Opt-in (bench.py and FlatTrainer switch it on): in TRAINING mode run conv 3->N 3x3 + bias + GDN of g_a as ONE kernel
+# Opt-in (bench.py switches it on; a training script does the same with `layers.FUSE_FIRST_LAYER = True`): in TRAINING mode run conv 3->N 3x3 + bias + GDN of g_a as ONE kernel
 # (F_sic.conv0_gdn: no C x H x W intermediate, backward recomputes it).  The fused convolution is fp32-accurate but not bit-identical
 # to cuDNN's, so the library default keeps the cuDNN + K2 path whose latents are pinned bit for bit against the reference, and eval /
 # compress never use the fused layer.
