@@ -482,7 +482,26 @@ def kernel_rooflines(cfg, dev, channels_last=True, fused_first_layer=True):
     xr = x.clone().requires_grad_(True)
     y = F.gdn(xr, beta, w, False)
     t = time_it(lambda: torch.autograd.grad(y, (xr, beta, w), g, retain_graph=True), big=12 * n >= (256 << 20))
-    out["gdn_bwd_channels_last_128"] = {"shape": list(x.shape), "bytes": 12 * n, "ms": t * 1e3, "gbs": 12 * n / t / 1e9}
+    out["gdn_bwd_channels_last_128"] = {"shape": list(x.shape), "bytes": 12 * n, "ms": t * 1e3, "gbs": 12 * n / t / 1e9,
+                                        "note": "both launches of the site's backward: gdn_bwd_nhwc_kernel + gdn_bwd_finalize_kernel"}
+    # the streaming kernel on its own (sic_gdn_bwd_partials: the C-ABI half that launches only gdn_bwd_nhwc_kernel), at both sites
+    import ctypes
+    from domain_specific_image_compression_b200 import _lib as _L
+    lib = _L.load()
+    vp = lambda tt: ctypes.c_void_p(tt.data_ptr())
+    for tag, xx, gg in (("gdn_bwd_nhwc_kernel_alone_128", x, g),):
+        Bq, Cq, Hq, Wq = xx.shape
+        ws = torch.zeros(lib.sic_gdn_bwd_workspace_bytes(Bq, Cq, Hq * Wq), dtype=torch.uint8, device=dev)
+        dxq = torch.empty_like(xx)
+        bq, wq = beta.detach(), w.detach().reshape(-1).contiguous()
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        def main_only():
+            rc = lib.sic_gdn_bwd_partials(vp(xx), None, vp(gg), vp(bq), vp(wq), Bq, Cq, Hq * Wq, 0, 1, vp(dxq), vp(ws), ws.numel(), st)
+            assert rc == 0, lib.sic_last_error()
+        t = time_it(main_only, big=12 * xx.numel() >= (256 << 20))
+        out[tag] = {"shape": list(xx.shape), "bytes": 12 * xx.numel(), "ms": t * 1e3, "gbs": 12 * xx.numel() / t / 1e9,
+                    "note": "gdn_bwd_nhwc_kernel only (dx + per-CTA partials), launched through sic_gdn_bwd_partials"}
+        del ws, dxq
     del x, g, xr, y
     # N2: the fused first analysis layer (image in, y out / grad_y in): algorithmic bytes = the activation tensor once + the image
     try:
@@ -563,7 +582,7 @@ def kernel_rooflines(cfg, dev, channels_last=True, fused_first_layer=True):
     # dram__bytes_write.sum of that kernel at this shape, looked up in profiles/ncu_traffic.json (written by scripts/ncu_traffic.py
     # from a committed ncu --set full capture) and used ONLY if the capture's registers/thread equal those of the loaded library.
     if channels_last and fused_first_layer:
-        dom, kid = out["gdn_bwd_channels_last_128"], "gdn_bwd_nhwc_kernel<0>"
+        dom, kid = out["gdn_bwd_nhwc_kernel_alone_128"], "gdn_bwd_nhwc_kernel<0>"
         kname = ("gdn_bwd_nhwc_kernel (GDN/IGDN backward, channels_last; 12 launches and the largest share of the step among our kernels: "
                  "profiles/r02h_ncu_launches_bench_step.txt) at its largest site in the step, 128^2 (the 256^2 site is inside the fused "
                  "first-layer kernel; this kernel at 256^2: kernels.gdn_bwd_channels_last)")
@@ -582,9 +601,11 @@ def kernel_rooflines(cfg, dev, channels_last=True, fused_first_layer=True):
     roof = {"kernel": kname, "bound": "hbm", "achieved": dom["gbs"], "peak": peak,
             "unit": "GB/s", "frac": dom["gbs"] / peak, "traffic": traffic, "traffic_source": tsrc, "registers_per_thread": regs,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": dom["bytes"], "ms_per_launch": dom["ms"],
-            "timing": "CUDA events on the launching stream around 10 back-to-back backward passes of the site (each = main kernel + the "
-                      "per-channel finalize launch), queued behind a 1 ms device-side spin so the host is a full queue ahead; working set "
-                      ">= 3 x the 126 MB L2, walked front to back: no flush needed, none done; time / 10, median of 3 batches"}
+            "site_backward_ms_incl_fold_launch": out.get("gdn_bwd_channels_last_128", {}).get("ms") if (channels_last and fused_first_layer) else None,
+            "timing": "CUDA events on the launching stream around 10 back-to-back launches of this kernel (through the C ABI: "
+                      "sic_gdn_bwd_partials when the first layer is fused, else the site's whole backward incl. the per-channel fold "
+                      "launch), queued behind a 1 ms device-side spin so the host is a full queue ahead; working set >= 3 x the 126 MB "
+                      "L2, walked front to back: no flush needed, none done; time / 10, median of 3 batches"}
     return roof, out
 
 

@@ -34,6 +34,8 @@ PROTOTYPES = {
     "sic_bottleneck_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "sic_gdn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "sic_gdn_bwd_workspace_bytes": (_z, [_i, _i, _i]),
+    "sic_gdn_bwd_partials": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _z, _p]),
+    "sic_gdn_bwd_fold": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
     "sic_gdn_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _z, _p]),
     "sic_gdn_dense_fwd": (_i, [_p, _p, _p, _l, _i, _i, _p, _p]),
     "sic_gdn_dense_fwd_variant": (_i, [_p, _p, _p, _l, _i, _i, _p, _i, _p]),

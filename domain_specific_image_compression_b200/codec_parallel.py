@@ -96,17 +96,54 @@ def compress_sharded(model, x: torch.Tensor, tail: int = 10, coder: str = "gpu",
     return merge_compressed(parts, B)
 
 
+def _is_nccl(group) -> bool:
+    import torch.distributed as dist
+    try:
+        return dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl"
+    except Exception:
+        return False
+
+
+def _gather_images_nccl(local: Optional[torch.Tensor], idx: Sequence[int], B: int, world: int, group, device) -> Optional[torch.Tensor]:
+    """Decoded images are the one thing of this path that is big (402 MB for 128 patches of 512^2): when every rank wants the
+    whole batch that IS an exchange step, so it goes over NVLink as one all_gather of equal-sized device blocks instead of being
+    pickled through the host (r02m: 1146 ms for 128 patches with all_gather_object).  Returns the batch in patch order on the
+    device.  Only called over an NCCL group (other backends keep the object gather)."""
+    import torch.distributed as dist
+    per = (B + world - 1) // world                                  # patches of rank 0 (the longest list)
+    meta = [None] * world
+    dist.all_gather_object(meta, None if local is None else tuple(local.shape[1:]), group=group)     # a few bytes
+    shape = next((m for m in meta if m is not None), None)
+    if shape is None:
+        raise ValueError("no rank decoded any patch")
+    block = torch.zeros((per,) + tuple(shape), dtype=torch.float32, device=device)
+    if local is not None:
+        block[: local.shape[0]] = local
+    allb = torch.empty((world * per,) + tuple(shape), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(allb, block, group=group)
+    # rank r's j-th patch is global patch r + j * world  ->  position r * per + j of the gathered blocks
+    order = torch.tensor([(i % world) * per + i // world for i in range(B)], dtype=torch.long, device=device)
+    return allb.index_select(0, order)
+
+
 def decompress_sharded(model, compressed: Dict, coder: str = "gpu", group=None, gather: bool = True,
-                       rank: Optional[int] = None, world: Optional[int] = None):
+                       rank: Optional[int] = None, world: Optional[int] = None, device_result: bool = False):
     """Rank r decodes patches r, r+W, ... of a (merged) compress() result.
-    gather=True: returns x_hat [B,3,H,W] as a HOST tensor in patch order on every rank.
-    gather=False: returns (indices, local x_hat on the model's device or None)."""
+    gather=True: returns x_hat [B,3,H,W] in patch order on every rank — a HOST tensor (device_result=False, the default) or the
+    device tensor itself (device_result=True).  Over an NCCL group the images travel as one device all_gather (NVLink) and are
+    copied to the host once; other backends (gloo: the CPU tests) gather pickled objects.
+    gather=False: returns (indices, local x_hat on the model's device or None) without any communication."""
     r, w = _rank_world(group, rank, world)
     B = len(compressed["strings"])
     idx = patch_indices(B, r, w)
     local = model.decompress(split_compressed(compressed, idx), coder=coder) if idx else None
     if not gather:
         return idx, local
+    if w > 1 and rank is None and _is_nccl(group):
+        dev = local.device if local is not None else torch.device("cuda", torch.cuda.current_device())   # an idle rank still takes part
+        full = _gather_images_nccl(local, idx, B, w, group, dev)
+        if full is not None:
+            return full if device_result else full.cpu()
     parts = _gather_objects((idx, None if local is None else local.cpu()), group, w)
     ref = next(p for _, p in parts if p is not None)
     out = torch.empty((B,) + tuple(ref.shape[1:]), dtype=ref.dtype)

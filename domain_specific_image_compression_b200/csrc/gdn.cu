@@ -382,9 +382,42 @@ extern "C" size_t sic_gdn_bwd_workspace_bytes(int B, int C, int HW) {
     return nchw > nhwc ? nchw : nhwc;
 }
 
+// number of partials per (array, channel) the main kernel leaves in the workspace for this shape and layout
+static long gdn_bwd_partials_per_channel(int B, int C, int HW, int channels_last) {
+    if (channels_last) return nhwc_bwd_grid((long)B * C * HW / 4, nhwc_threads(C));
+    return (long)B * bwd_chunks(HW);
+}
+
+extern "C" int sic_gdn_bwd_fold(const float *beta_param, const float *gamma_weight, int B, int C, int HW, int channels_last, float *dbias,
+                                float *dbeta_param, float *dgamma_weight, const void *workspace, size_t workspace_bytes, void *stream) {
+    SIC_CHECK_ARG(B > 0 && C > 0 && HW > 0, "sic_gdn_bwd_fold: empty shape B=%d C=%d HW=%d", B, C, HW);
+    SIC_CHECK_ARG(beta_param && gamma_weight && workspace, "sic_gdn_bwd_fold: null pointer");
+    if (workspace_bytes < sic_gdn_bwd_workspace_bytes(B, C, HW)) {
+        set_error("sic_gdn_bwd_fold: workspace %zu < %zu bytes", workspace_bytes, sic_gdn_bwd_workspace_bytes(B, C, HW));
+        return SIC_E_WORKSPACE;
+    }
+    if (channels_last && (C % 4 != 0 || C > 4 * kThreads)) {
+        set_error("sic_gdn_bwd_fold: channels_last needs C %% 4 == 0 and C <= %d", 4 * kThreads);
+        return SIC_E_UNSUPPORTED;
+    }
+    const long P = gdn_bwd_partials_per_channel(B, C, HW, channels_last);
+    gdn_bwd_finalize_kernel<<<dim3(C, 3), kFinThreads, 0, (cudaStream_t)stream>>>(static_cast<const float *>(workspace), beta_param, gamma_weight, C, P,
+                                                                                  dbeta_param, dgamma_weight, dbias);
+    SIC_CHECK_LAUNCH("sic_gdn_bwd_fold");
+    return 0;
+}
+
 extern "C" int sic_gdn_bwd(const float *x, const float *bias, const float *g, const float *beta_param, const float *gamma_weight,
                            int B, int C, int HW, int inverse, int channels_last, float *dx, float *dbias, float *dbeta_param,
                            float *dgamma_weight, void *workspace, size_t workspace_bytes, void *stream) {
+    int rc = sic_gdn_bwd_partials(x, bias, g, beta_param, gamma_weight, B, C, HW, inverse, channels_last, dx, workspace, workspace_bytes, stream);
+    if (rc != 0) return rc;
+    return sic_gdn_bwd_fold(beta_param, gamma_weight, B, C, HW, channels_last, dbias, dbeta_param, dgamma_weight, workspace, workspace_bytes, stream);
+}
+
+extern "C" int sic_gdn_bwd_partials(const float *x, const float *bias, const float *g, const float *beta_param, const float *gamma_weight,
+                                    int B, int C, int HW, int inverse, int channels_last, float *dx, void *workspace, size_t workspace_bytes,
+                                    void *stream) {
     SIC_CHECK_ARG(B > 0 && C > 0 && HW > 0, "sic_gdn_bwd: empty shape B=%d C=%d HW=%d", B, C, HW);
     SIC_CHECK_ARG(x && g && dx && beta_param && gamma_weight && workspace, "sic_gdn_bwd: null pointer");
     if (workspace_bytes < sic_gdn_bwd_workspace_bytes(B, C, HW)) {
@@ -407,8 +440,6 @@ extern "C" int sic_gdn_bwd(const float *x, const float *bias, const float *g, co
         if (inverse) gdn_bwd_nhwc_kernel<true><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, iters, (float4 *)dx, part);
         else gdn_bwd_nhwc_kernel<false><<<grid, threads, smem, st>>>((const float4 *)x, bias, (const float4 *)g, beta_param, gamma_weight, n4, C, iters, (float4 *)dx, part);
         SIC_CHECK_LAUNCH("sic_gdn_bwd (nhwc)");
-        gdn_bwd_finalize_kernel<<<dim3(C, 3), kFinThreads, 0, st>>>(part, beta_param, gamma_weight, C, (long)grid, dbeta_param, dgamma_weight, dbias);
-        SIC_CHECK_LAUNCH("sic_gdn_bwd finalize");
         return 0;
     }
     const int chunks = bwd_chunks(HW);
@@ -423,7 +454,5 @@ extern "C" int sic_gdn_bwd(const float *x, const float *bias, const float *g, co
         else gdn_bwd_kernel<false, false><<<(unsigned)units, kThreads, 0, st>>>(x, bias, g, beta_param, gamma_weight, C, HW, chunks, dx, part);
     }
     SIC_CHECK_LAUNCH("sic_gdn_bwd");
-    gdn_bwd_finalize_kernel<<<dim3(C, 3), kFinThreads, 0, st>>>(part, beta_param, gamma_weight, C, (long)B * chunks, dbeta_param, dgamma_weight, dbias);
-    SIC_CHECK_LAUNCH("sic_gdn_bwd finalize");
     return 0;
 }

@@ -99,6 +99,14 @@ int sic_bottleneck_bwd(const float *y_tilde, const float *mu, const float *sigma
 int sic_gdn_fwd(const float *x, const float *bias, const float *beta_param, const float *gamma_weight, int B, int C, int HW,
                 int inverse, int channels_last, float *y, void *stream);
 size_t sic_gdn_bwd_workspace_bytes(int B, int C, int HW);
+/* sic_gdn_bwd = sic_gdn_bwd_partials (the streaming kernel: dx, and per-CTA partial sums of d(beta), d(gamma), d(bias) left in the
+ * workspace) followed by sic_gdn_bwd_fold (fixed-order binary64 fold of those partials + chain rule through the squared
+ * re-parameterisation) on the same stream.  The two halves are exported so that each kernel can be timed on its own. */
+int sic_gdn_bwd_partials(const float *x, const float *bias, const float *g, const float *beta_param, const float *gamma_weight, int B,
+                         int C, int HW, int inverse, int channels_last, float *dx, void *workspace, size_t workspace_bytes,
+                         void *stream);
+int sic_gdn_bwd_fold(const float *beta_param, const float *gamma_weight, int B, int C, int HW, int channels_last, float *dbias,
+                     float *dbeta_param, float *dgamma_weight, const void *workspace, size_t workspace_bytes, void *stream);
 int sic_gdn_bwd(const float *x, const float *bias, const float *g, const float *beta_param, const float *gamma_weight, int B,
                 int C, int HW, int inverse, int channels_last, float *dx, float *dbias, float *dbeta_param,
                 float *dgamma_weight, void *workspace, size_t workspace_bytes, void *stream);

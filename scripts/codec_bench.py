@@ -69,7 +69,13 @@ if world > 1:
     assert len(merged["strings"]) == B * world
     assert torch.equal(xh_all[idx].to(dev), ref["x_hat"].clamp(0, 1)), "sharded round trip differs from forward() on this rank's patches"
     res["sharded_api_with_host_gather"] = {"compress_ms": tcs * 1e3, "decompress_ms": tds * 1e3,
-                                           "compress_patches_per_s": B * world / tcs, "decompress_patches_per_s": B * world / tds}
+                                           "compress_patches_per_s": B * world / tcs, "decompress_patches_per_s": B * world / tds,
+                                           "note": "decompress: every rank ends with ALL reconstructions as a HOST tensor (NCCL all_gather on the "
+                                                   "device, then one pageable D2H copy of the whole batch)"}
+    tdd, xh_dev = timed(lambda: CP.decompress_sharded(m, merged, device_result=True), reps=3)
+    assert torch.equal(xh_dev[idx], ref["x_hat"].clamp(0, 1))
+    res["sharded_api_device_gather"] = {"decompress_ms": tdd * 1e3, "decompress_patches_per_s": B * world / tdd,
+                                        "note": "every rank ends with all reconstructions on its device (one all_gather over NVLink)"}
 with torch.no_grad():
     loss, R, D = sic.rate_distortion_loss(ref, x, 1.0, "mse")
 res["bpp_estimated_density_rank0"] = float(R)

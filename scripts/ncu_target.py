@@ -93,3 +93,39 @@ if which_set & {"deconv"}:
         yv = F.deconv_rgb(a, w, bias)
         torch.autograd.grad(yv, (a, w, bias), torch.randn_like(yv))
     del a, yv
+if which_set & {"gdn128"}:
+    x = torch.randn(16, 128, 128, 128, device=dev).contiguous(memory_format=torch.channels_last)
+    g = torch.randn_like(x)
+    beta = torch.sqrt(torch.rand(128, device=dev) + 0.5).requires_grad_(True)
+    w = torch.sqrt(torch.rand(128, 1, 1, 1, device=dev) * 0.3 + 0.01).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    for _ in range(reps):
+        for inv in (False, True):
+            yv = F.gdn(xr, beta, w, inv)
+            torch.autograd.grad(yv, (xr, beta, w), g)
+    del x, g, xr, yv
+if which_set & {"ssim"}:
+    import domain_specific_image_compression_b200 as sic
+    a = torch.rand(16, 3, 256, 256, device=dev).requires_grad_(True)
+    b = torch.rand(16, 3, 256, 256, device=dev)
+    for _ in range(reps):
+        v = sic.losses.multi_scale_ssim(a, b, data_range=1.0, scale_weights=[0.3, 0.5, 0.2])
+        torch.autograd.grad(v, a)
+if which_set & {"codec"}:
+    import domain_specific_image_compression_b200 as sic
+    import bench
+    torch.manual_seed(42)
+    m = sic.CompressionModel(N=128, M=192, min_nu=2.0).to(dev).eval()
+    with torch.no_grad():
+        m.g_a.g_a[14].weight.mul_(40.0); m.h_a.h_a[6].weight.mul_(40.0); m.h_s.mlp_nu[2].bias.add_(1.5)
+    xb = bench.synthetic_batch(4, 512, 512, 7, dev)
+    for _ in range(reps):
+        c = m.compress(xb)
+        m.decompress(c)
+if which_set & {"hyper"}:
+    import domain_specific_image_compression_b200 as sic
+    hs = sic.layers.HyperSynthesis(128, 192).to(dev)
+    t = torch.relu(torch.randn(16, 128, 16, 16, device=dev)).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    for _ in range(reps):
+        sg, nu = F.hyper_tail(t, hs.mlp_sigma, hs.mlp_nu, 2.0, 100.0)
+        torch.autograd.grad((sg.sum() + nu.sum()), [t] + list(hs.mlp_sigma.parameters()) + list(hs.mlp_nu.parameters()))
