@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--no-fuse-first-layer", action="store_true", help="keep g_a's first layer as cuDNN conv + GDN kernel (default: the fused "
                     "conv 3->N 3x3 + bias + GDN tcgen05 kernel, forward and backward: layers.FUSE_FIRST_LAYER)")
+    ap.add_argument("--no-overlap-hyper", action="store_true", help="run the hyperprior branch in line with the synthesis transform "
+                    "(default: on a side stream next to it, forward and backward: model.OVERLAP_HYPER_BRANCH)")
     ap.add_argument("--no-fast-last-layer", action="store_true", help="keep g_s's last layer deconv(N,3) on cuDNN (default: library GEMM + "
                     "the col2im / im2col gather kernels: layers.FAST_LAST_LAYER)")
     ap.add_argument("--pad-rgb", type=int, default=0, choices=[0, 4, 8], help="zero-pad the image-side channel axis of the first conv / "
@@ -263,6 +265,8 @@ def run_ours(args):
         _layers.PAD_RGB_CHANNELS = args.pad_rgb
     _layers.FUSE_FIRST_LAYER = not (args.no_fuse_first_layer or args.pad_rgb or args.gdn == "dense" or args.nchw)
     _layers.FAST_LAST_LAYER = not (args.no_fast_last_layer or args.pad_rgb or args.nchw)
+    from domain_specific_image_compression_b200 import model as _model
+    _model.OVERLAP_HYPER_BRANCH = not args.no_overlap_hyper
     model = model.to(memory_format=fmt)
     trainer = FlatTrainer(model, lr=1e-4, betas=(0.9, 0.999), grad_clip=1.0, bucket_bytes=int(args.bucket_mb * (1 << 20)))
     x_dev = synthetic_batch(B, H, W, 42 + rank, dev).contiguous(memory_format=fmt)
@@ -379,7 +383,7 @@ def run_ours(args):
                        "l2": "per-step working set (>= 5 GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "conv_math": "cuDNN fp32 with TF32 allowed (PyTorch default, as the reference)",
                        "activation_layout": "NCHW" if args.nchw else "channels_last", "launch": graph_note,
-                       "rgb_channel_padding": args.pad_rgb, "gdn": args.gdn, "fused_first_layer": bool(_layers.FUSE_FIRST_LAYER), "gemm_last_layer": bool(_layers.FAST_LAST_LAYER),
+                       "rgb_channel_padding": args.pad_rgb, "gdn": args.gdn, "fused_first_layer": bool(_layers.FUSE_FIRST_LAYER), "gemm_last_layer": bool(_layers.FAST_LAST_LAYER), "hyper_branch_on_side_stream": bool(_model.OVERLAP_HYPER_BRANCH),
                        "gradient_buckets": [hi - lo for lo, hi, _, _ in trainer.buckets] if world > 1 else None,
                        "cudnn_benchmark": not args.no_cudnn_benchmark},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world,

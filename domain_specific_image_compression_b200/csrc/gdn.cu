@@ -316,7 +316,21 @@ inline int nhwc_iters(long n4, int per_pass, int max_iters) {
     long it = n4 / ((long)per_pass * sm_count() * 8);
     return (int)(it < 1 ? 1 : (it > max_iters ? max_iters : it));
 }
-inline int nhwc_bwd_iters(long n4, int threads) { return nhwc_iters(n4, threads * kBwdNhwcU, n4 > (16L << 20) ? 16 : 8); }
+// Backward: 4 resident CTAs per SM (launch bounds).  Among the pass counts between half the cap and the cap, take the one whose grid
+// fills its last wave best: at the 128^2 sites the cap (8 passes) gives 2048 CTAs = 3.46 waves of 592, 7 passes give 2341 = 3.95.
+inline int nhwc_bwd_iters(long n4, int threads) {
+    const int cap = nhwc_iters(n4, threads * kBwdNhwcU, n4 > (16L << 20) ? 16 : 8);
+    const long slots = 4L * sm_count();
+    int best = cap;
+    double best_fill = -1.0;
+    for (int it = cap; it >= (cap + 1) / 2 && it >= 1; --it) {
+        const long chunk = (long)threads * kBwdNhwcU * it, grid = (n4 + chunk - 1) / chunk;
+        const long waves = (grid + slots - 1) / slots;
+        const double fill = (double)grid / (double)(waves * slots);
+        if (fill > best_fill + 0.02) { best_fill = fill; best = it; }   // prefer more passes per CTA (fewer partials) unless clearly better
+    }
+    return best;
+}
 inline long nhwc_bwd_grid(long n4, int threads) {
     const long chunk = (long)threads * kBwdNhwcU * nhwc_bwd_iters(n4, threads);
     return (n4 + chunk - 1) / chunk;

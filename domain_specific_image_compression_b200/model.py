@@ -22,6 +22,36 @@ from .layers import AnalysisTransform, HyperAnalysis, HyperSynthesis, SynthesisT
 from .losses import multi_scale_ssim
 
 
+# Opt-in (bench.py switches it on): in TRAINING mode run the hyperprior branch (h_a -> K1(z) -> h_s -> tail -> K1 likelihood of y)
+# on a side stream next to the synthesis transform.  The two branches only share y / y_tilde: g_s(y_tilde) does not need sigma / nu,
+# and the likelihood does not need x_hat.  The hyper branch is ~40 launches on 16x16 ... 4x4 maps (latency-bound, a few CTAs each)
+# which otherwise sit in line between the large analysis and synthesis kernels, forward and backward (autograd runs each backward
+# node on its forward's stream).  Same values as the sequential schedule: y_tilde is produced first by the quantise-only form of K1
+# (same arithmetic), the likelihood kernel then takes y_tilde with quant = none.
+OVERLAP_HYPER_BRANCH = False
+_side_streams = {}
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+    """The per-device side stream of the overlapped schedule (created on first use)."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _side_streams.get(idx)
+    if st is None:
+        st = _side_streams[idx] = torch.cuda.Stream(device=idx)
+    return st
+
+
+def join_side_streams(device) -> None:
+    """Make the current stream wait for everything queued on the side stream so far (no-op if the overlapped schedule never ran).
+    FlatTrainer calls it before it packs a gradient bucket: the bucket's gradients may have been produced on either stream."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _side_streams.get(idx)
+    if st is not None:
+        torch.cuda.current_stream(idx).wait_stream(st)
+
+
 FUSE_HYPER_TAIL = True      # False: run the hyper-synthesis tail as the reference's eager op chain (layers.py:141-152, model.py:54-55)
 
 
@@ -71,6 +101,8 @@ class CompressionModel(nn.Module):
         if quant_mode not in ("noise", "round"):
             raise ValueError(f"Unknown quant mode: {quant_mode}")
         y = self.g_a(x)
+        if OVERLAP_HYPER_BRANCH and self.training and quant_mode == "noise" and y.is_cuda:
+            return self._forward_overlapped(y, noise_y, noise_z)
         z = self.h_a(y)
         # K1 (Gaussian): quantise z + nll_z + per-patch bits in one launch (model.py:45,59)
         z_tilde, nll_z, bits_z = F_sic.bottleneck(z, self.z_prior.log_sigma, quant=quant_mode, lik="gaussian", noise=noise_z)
@@ -83,6 +115,28 @@ class CompressionModel(nn.Module):
         else:
             y_hat = y_tilde if quant_mode == "round" else torch.round(y)   # round(y) twice in the reference; identical bits
         x_hat = self.g_s(y_hat)
+        return {"x_hat": x_hat, "nll_y": nll_y, "nll_z": nll_z, "y": y, "y_tilde": y_tilde, "z": z, "z_tilde": z_tilde,
+                "sigma": sigma, "nu": nu}
+
+    def _forward_overlapped(self, y, noise_y, noise_z):
+        """Training forward with the hyperprior branch on a side stream (OVERLAP_HYPER_BRANCH).  Same nine outputs."""
+        cur = torch.cuda.current_stream(y.device)
+        side = side_stream(y.device)
+        # y_tilde first (model.py:44), so that the synthesis transform can start: quantise-only K1, or the supplied draw
+        y_tilde = (y + noise_y) if noise_y is not None else F_sic.quantize(y, "noise")
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            z = self.h_a(y)
+            z_tilde, nll_z, bits_z = F_sic.bottleneck(z, self.z_prior.log_sigma, quant="noise", lik="gaussian", noise=noise_z)
+            sigma_k, nu_k, sigma, nu = self._student_params(z_tilde, y)
+            _, nll_y, bits_y = F_sic.bottleneck(y_tilde, sigma_k, nu_k, quant="none", lik=self.likelihood)
+            nll_y._sic_bits, nll_z._sic_bits = bits_y, bits_z
+        for t in (y, y_tilde):
+            t.record_stream(side)
+        x_hat = self.g_s(y_tilde)
+        cur.wait_stream(side)
+        for t in (z, z_tilde, nll_z, nll_y, bits_y, bits_z, sigma_k, nu_k):
+            t.record_stream(cur)
         return {"x_hat": x_hat, "nll_y": nll_y, "nll_z": nll_z, "y": y, "y_tilde": y_tilde, "z": z, "z_tilde": z_tilde,
                 "sigma": sigma, "nu": nu}
 

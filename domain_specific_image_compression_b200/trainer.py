@@ -117,6 +117,9 @@ class FlatTrainer:
     def _fire(self, k: int) -> None:
         """Every gradient of bucket k exists: pack them into the bucket's slice of the flat buffer and start its all-reduce."""
         lo, hi, a, b = self.buckets[k]
+        if self.flat_grad.is_cuda:             # gradients of one bucket may come from the model's side stream (model.OVERLAP_HYPER_BRANCH)
+            from .model import join_side_streams
+            join_side_streams(self.flat_grad.device)
         torch.cat([_flat_in_param_order(self.live[i].grad, self.live[i]) for i in range(a, b)], out=self.flat_grad[lo:hi])
         self.fire_order.append(k)
         if self.world > 1:                     # asynchronous: runs on the collective's own stream under the rest of backward()

@@ -262,3 +262,43 @@ def test_training_step_under_autocast_like_the_reference(golden):
     scaler.scale(loss).backward()
     live = [(n, p) for n, p in m.named_parameters() if not n.endswith(".gamma")]
     assert all(p.grad is not None and p.grad.dtype == torch.float32 and torch.isfinite(p.grad).all() for _, p in live)
+
+
+def test_overlapped_hyper_branch_matches_sequential_schedule(golden):
+    """model.OVERLAP_HYPER_BRANCH: the hyperprior branch on a side stream next to the synthesis transform.  With the same supplied
+    noise the nine outputs are bit-identical to the sequential schedule (y_tilde = y + noise either way; the likelihood kernel sees
+    the same y_tilde), the loss is equal and the gradients agree to summation order (three gradient contributions meet at y)."""
+    import domain_specific_image_compression_b200 as sic
+    from domain_specific_image_compression_b200 import model as M_
+    m, G = _model(golden)
+    m.train()
+    x = torch.from_numpy(G["x"]).cuda()
+    ny, nz = torch.from_numpy(G["train.noise_y"]).cuda(), torch.from_numpy(G["train.noise_z"]).cuda()
+    res = {}
+    try:
+        for ov in (False, True):
+            M_.OVERLAP_HYPER_BRANCH = ov
+            m.zero_grad(set_to_none=True)
+            with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True):
+                out = m(x, "noise", noise_y=ny, noise_z=nz)
+                loss, Rr, D = sic.rate_distortion_loss(out, x, 100.0, "msssim")
+                loss.backward()
+            torch.cuda.synchronize()
+            res[ov] = ({k: v.detach().clone() for k, v in out.items()}, float(loss), float(Rr),
+                       {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
+        # Philox path (no supplied noise): runs, finite, fresh noise per call
+        M_.OVERLAP_HYPER_BRANCH = True
+        a = m(x, "noise")
+        b = m(x, "noise")
+        torch.cuda.synchronize()
+        assert not torch.equal(a["y_tilde"], b["y_tilde"]) and torch.isfinite(a["nll_y"]).all()
+        assert float((a["y_tilde"] - a["y"]).abs().max()) <= 0.5
+    finally:
+        M_.OVERLAP_HYPER_BRANCH = False
+    (o0, l0, r0, g0), (o1, l1, r1, g1) = res[False], res[True]
+    for k in o0:
+        assert torch.equal(o0[k], o1[k]), k
+    assert l0 == l1 and r0 == r1
+    assert g0.keys() == g1.keys()
+    for n in g0:
+        assert float((g0[n] - g1[n]).abs().max()) <= 1e-5 * float(g0[n].abs().max()) + 1e-9, n
