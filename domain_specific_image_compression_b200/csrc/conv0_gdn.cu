@@ -19,8 +19,10 @@
 //                        x 4 K-steps of 8.  Backward, GEMM 2: dW[c, k] += sum_p dv[c, p] patch[p, k] with dv read FROM TENSOR MEMORY
 //                        (the .ts MMA form: lane = channel, column = position is exactly how the epilogue holds dv) into a per-tile
 //                        accumulator that the epilogue warps drain into a shared-memory running sum (see `sdw`)
-//   epilogue (16 warps)  forward: TMEM -> + bias -> GDN -> y.  Backward: TMEM v + global g -> dv = g beta / d^3, per-lane sums of
-//                        d(beta), d(gamma), d(bias); dv split exactly into hi (stored over v, in place) and lo (third TMEM region)
+//   bias                 rides in the GEMMs: im2col column 27 is the constant 1 and weight column 27 is the bias, so GEMM 1 returns
+//                        conv + bias and GEMM 2 returns d(bias) = sum dv in column 27 of dW - no per-element add, no per-lane sum
+//   epilogue (16 warps)  forward: TMEM -> GDN -> y.  Backward: TMEM v + global g -> dv = g beta / d^3, per-lane sums of
+//                        d(beta), d(gamma); dv split exactly into hi (stored over v, in place) and lo (third TMEM region)
 //   end of kernel        per-CTA partials of dW and of the three per-channel sums; a second tiny kernel folds the <= 148 partials in a
 //                        fixed order (binary64, deterministic, no atomics) and applies the chain rule to the stored parameters.
 // C <= 128: one M = 128 block, 128 positions per tile.  C == 192: two M = 128 blocks (rows >= 192 zero), 64 positions per tile.
@@ -44,6 +46,7 @@ constexpr int kC0EpiThreads = kC0Epi * 32, kC0ProdThreads = kC0Prod * 32;
 constexpr int kC0Threads = kC0EpiThreads + kC0ProdThreads + 32;
 constexpr int kC0K = 27;                 // 3 x 3 x 3 taps, K index = (kh * 3 + kw) * 3 + cin (channels-last order of weight and image)
 constexpr int kC0KP = 32;                // K padded to one 128-byte swizzle row
+constexpr int kC0One = 27;               // the constant-one column of the im2col rows (weight column = bias)
 
 template <int C, bool BWD>
 struct C0Cfg {
@@ -105,15 +108,19 @@ __device__ __forceinline__ float ldg_stream1(const float *p) {
 }
 
 // weights -> A operand (hi, lo), K-major SWIZZLE_128B, one 128-byte row per output channel; rows >= C are zero
+// K column 27 carries the bias: the im2col rows hold 1.0 there (kC0One), so GEMM 1 adds the bias and GEMM 2 returns d(bias) = sum dv
 template <int ROWS_W>
-__device__ __forceinline__ void stage_weights(const float *__restrict__ w, int C, uint32_t sWh, uint32_t sWl, int tid) {
+__device__ __forceinline__ void stage_weights(const float *__restrict__ w, const float *__restrict__ bias, int C, uint32_t sWh, uint32_t sWl,
+                                              int tid) {
     for (int idx = tid; idx < ROWS_W * 8; idx += kC0Threads) {
         const int i = idx >> 3, c = idx & 7;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (i < C) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 4; ++j) {
                 if (4 * c + j < kC0K) v[j] = __ldg(w + (size_t)i * kC0K + 4 * c + j);
+                else if (4 * c + j == kC0One && bias != nullptr) v[j] = __ldg(bias + i);
+            }
         }
         float4 hi, lo;
         split4(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
@@ -137,7 +144,7 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
     // barriers: full1[NS1], empty1[NS1], full2[NS2], empty2[NS2], tfull[2], tempty[2] (fwd) / dvfull[2] (bwd), dvlo_empty, done
     __shared__ __align__(8) uint64_t bars[2 * NS1 + 2 * NS2 + 6];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float red[BWD ? 4 * MB * 128 * 3 : 1];
+    __shared__ float red[BWD ? 4 * MB * 128 * 2 : 1];
     // dW of this CTA, [block][k][channel row]: GEMM 2 starts a FRESH tensor-memory accumulator every tile and the epilogue warps
     // add it in here with round-to-nearest fp32 adds.  One accumulator for the whole kernel (first version) is biased: the tensor
     // core truncates when it adds into a large running sum, and over ~2600 accumulating MMAs per CTA at the 16 x 256^2 site dW came
@@ -148,7 +155,7 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
     const uint32_t bar_full2 = smem_u32(&bars[2 * NS1]), bar_empty2 = smem_u32(&bars[2 * NS1 + NS2]);
     const uint32_t bar_tfull = smem_u32(&bars[2 * NS1 + 2 * NS2]), bar_epi = bar_tfull + 16;   // tempty (fwd) / dvfull (bwd)
     const uint32_t bar_dvlo = bar_epi + 16, bar_done = bar_dvlo + 8;
-    stage_weights<Cfg::ROWS_W>(w, C, sWh, sWl, tid);
+    stage_weights<Cfg::ROWS_W>(w, bias, C, sWh, sWl, tid);
     if (BWD) {
         for (int i = tid; i < MB * kC0KP * 128; i += kC0Threads) sdw[i] = 0.f;
     }
@@ -187,14 +194,14 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
     if (warp < kC0Epi) {
         // ===================================================== epilogue
         const int q = warp & 3, cg = warp >> 2;
-        float beta[MB], gamma[MB], bia[MB];
-        float sum_b[MB], sum_g[MB], sum_v[MB];
+        float beta[MB], gamma[MB];
+        float sum_b[MB], sum_g[MB];
 #pragma unroll
         for (int blk = 0; blk < MB; ++blk) {
             const int ch = blk * 128 + q * 32 + lane;
-            beta[blk] = 1.f; gamma[blk] = 0.f; bia[blk] = -0.0f;
-            sum_b[blk] = sum_g[blk] = sum_v[blk] = 0.f;
-            if (ch < C) { eff_params(beta_param, gamma_weight, ch, beta[blk], gamma[blk]); bia[blk] = load_bias(bias, ch); }
+            beta[blk] = 1.f; gamma[blk] = 0.f;
+            sum_b[blk] = sum_g[blk] = 0.f;
+            if (ch < C) eff_params(beta_param, gamma_weight, ch, beta[blk], gamma[blk]);
         }
         auto drain_dw = [&]() {   // this warp's 8 of the 32 k columns of the per-tile dW accumulator -> += into shared memory
 #pragma unroll
@@ -236,14 +243,14 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
                             if (whole && v_out == nullptr) {       // the hot path: 6 instructions per element
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) {
-                                    const float v = acc[j] + bia[blk];
+                                    const float v = acc[j];              // conv + bias (the bias came through the ones column)
                                     __stcs(yp + (size_t)j * C, v * rsqrt_fast(fmaf(gamma[blk], v * v, beta[blk])));   // training path, see header
                                 }
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) {
                                     if (k0 + j < left) {
-                                        const float v = acc[j] + bia[blk];
+                                        const float v = acc[j];
                                         if (v_out != nullptr) __stcs(v_out + (size_t)(p0 + k0 + j) * C + ch, v);
                                         __stcs(yp + (size_t)j * C, v * rsqrt_fast(fmaf(gamma[blk], v * v, beta[blk])));
                                     }
@@ -264,15 +271,14 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
                         float lo[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {             // GDN backward (gdn_math.cuh gdn_bwd1<false>) with the one-MUFU rsqrt;
-                            const float v = acc[j] + bia[blk];     // the constant factors (-1/2, beta) of the three sums are applied once, at the end
+                            const float v = acc[j];                 // conv + bias; the constant factor -1/2 of the two sums is applied once, at the end
                             const float x2 = v * v;
                             const float r = rsqrt_fast(fmaf(gamma[blk], x2, beta[blk]));
                             const float gr3 = gq[j] * (r * r * r);  // g / d^3; gq = 0 past the end: no contribution
                             const float t = gr3 * v;
                             sum_b[blk] += t;                        // d(beta)  = -1/2 sum g v / d^3
                             sum_g[blk] = fmaf(t, x2, sum_g[blk]);   // d(gamma) = -1/2 sum g v^3 / d^3
-                            sum_v[blk] += gr3;                      // d(bias)  = beta sum g / d^3
-                            const float dv = gr3 * beta[blk];
+                            const float dv = gr3 * beta[blk];       // d(bias) = sum dv comes out of GEMM 2 (ones column)
                             acc[j] = tf32_hi(dv);
                             lo[j] = dv - acc[j];
                         }
@@ -297,8 +303,8 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
             drain_dw();
 #pragma unroll
             for (int blk = 0; blk < MB; ++blk) {
-                float *r = red + ((cg * MB + blk) * 128 + q * 32 + lane) * 3;
-                r[0] = -0.5f * sum_b[blk]; r[1] = -0.5f * sum_g[blk]; r[2] = beta[blk] * sum_v[blk];
+                float *r = red + ((cg * MB + blk) * 128 + q * 32 + lane) * 2;
+                r[0] = -0.5f * sum_b[blk]; r[1] = -0.5f * sum_g[blk];
             }
         }
     } else if (warp < kC0Epi + kC0Prod) {
@@ -306,10 +312,12 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
         const int pp = tid - kC0EpiThreads;
         const bool active = pp < TN;
         float pn[kC0K];
+        float one = 0.f;                                            // 1.0 for a position inside the batch, else 0 (its whole row is zero)
         auto request = [&](long t) {
 #pragma unroll
             for (int k = 0; k < kC0K; ++k) pn[k] = 0.f;
             const long p = t * TN + pp;
+            one = (active && p < g.P) ? 1.f : 0.f;
             if (active && p < g.P) {
                 const int hw = g.H * g.W;
                 const int b = (int)(p / hw), rem = (int)(p - (long)b * hw);
@@ -353,7 +361,7 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
                     v4.x = 4 * c + 0 < kC0K ? pn[(4 * c + 0) % kC0K] : 0.f;
                     v4.y = 4 * c + 1 < kC0K ? pn[(4 * c + 1) % kC0K] : 0.f;
                     v4.z = 4 * c + 2 < kC0K ? pn[(4 * c + 2) % kC0K] : 0.f;
-                    v4.w = 4 * c + 3 < kC0K ? pn[(4 * c + 3) % kC0K] : 0.f;
+                    v4.w = 4 * c + 3 < kC0K ? pn[(4 * c + 3) % kC0K] : (4 * c + 3 == kC0One ? one : 0.f);
                     float4 hi, lo;
                     split4(v4, hi, lo);
                     const uint32_t off = sw128_offset(pp, 0, c, TN);
@@ -375,6 +383,8 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
                         sts32(sPht + off, hi);
                         sts32(sPlt + off, pn[k] - hi);
                     }
+                    // the ones row (its lo part stays zero from the start-up clear)
+                    sts32(sPht + sw128_offset(kC0One, pp >> 5, (pp & 31) >> 2, kC0KP) + (uint32_t)((pp & 3) << 2), one);
                 }
                 fence_proxy_async();
                 mbar_arrive(bar_full2 + 8 * s2);
@@ -452,13 +462,13 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
     __syncthreads();
     if (BWD) {
         // ===================================================== read-out: per-CTA partials
-        for (int i = tid; i < MB * 128 * 3; i += kC0Threads) {      // the three per-channel sums: fixed order over the four column groups
-            const int row = i / 3, which = i - row * 3;               // row = blk * 128 + channel-in-block = channel
+        for (int i = tid; i < MB * 128 * 2; i += kC0Threads) {      // the two per-channel sums: fixed order over the four column groups
+            const int row = i / 2, which = i - row * 2;               // row = blk * 128 + channel-in-block = channel
             if (row < C) {
                 float sacc = 0.f;
 #pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) sacc += red[((c4 * MB + row / 128) * 128 + (row & 127)) * 3 + which];
-                part_sums[(size_t)blockIdx.x * 3 * C + (size_t)which * C + row] = sacc;
+                for (int c4 = 0; c4 < 4; ++c4) sacc += red[((c4 * MB + row / 128) * 128 + (row & 127)) * 2 + which];
+                part_sums[(size_t)blockIdx.x * 2 * C + (size_t)which * C + row] = sacc;
             }
         }
         for (int i = tid; i < MB * 128 * kC0KP; i += kC0Threads) {
@@ -473,26 +483,27 @@ conv0_gdn_kernel(const float *__restrict__ x, const float *__restrict__ w, const
 }
 
 // fixed-order fold of the per-CTA partials (binary64) + chain rule to the stored parameters (layers.py:20-21):
-//   dW[c][k] = sum parts;  dbias = sum dv;  dbeta_param = 2 beta_param sum h;  dgamma_weight = 2 w sum h v^2
+//   dW[c][k] = sum parts (k < 27);  dbias[c] = sum parts of the ones column;  dbeta_param = 2 beta_param sum h;  dgamma_weight = 2 w sum h v^2
 __global__ void __launch_bounds__(256) conv0_gdn_bwd_finalize_kernel(const float *__restrict__ part_dw, const float *__restrict__ part_sums,
                                                                    int n_part, int C, const float *__restrict__ beta_param,
                                                                    const float *__restrict__ gamma_weight, float *__restrict__ dw,
                                                                    float *__restrict__ dbias, float *__restrict__ dbeta,
                                                                    float *__restrict__ dgamma) {
     const int e = blockIdx.x * 256 + threadIdx.x;
-    const int n_dw = C * kC0K;
+    const int n_dw = C * (kC0K + 1);
     if (e < n_dw) {
-        const int c = e / kC0K, k = e - c * kC0K;
+        const int c = e / (kC0K + 1), k = e - c * (kC0K + 1);       // k == 27: the ones column = d(bias)
+        if (k == kC0One && dbias == nullptr) return;
         double s = 0.0;
         for (int p = 0; p < n_part; ++p) s += (double)part_dw[((size_t)p * C + c) * kC0KP + k];
-        dw[e] = (float)s;
-    } else if (e < n_dw + 3 * C) {
+        if (k == kC0One) dbias[c] = (float)s;
+        else dw[c * kC0K + k] = (float)s;
+    } else if (e < n_dw + 2 * C) {
         const int r = e - n_dw, which = r / C, c = r - which * C;
         double s = 0.0;
-        for (int p = 0; p < n_part; ++p) s += (double)part_sums[(size_t)p * 3 * C + r];
+        for (int p = 0; p < n_part; ++p) s += (double)part_sums[(size_t)p * 2 * C + r];
         if (which == 0) dbeta[c] = (float)(2.0 * (double)beta_param[c] * s);
-        else if (which == 1) dgamma[c] = (float)(2.0 * (double)gamma_weight[c] * s);
-        else if (dbias != nullptr) dbias[c] = (float)s;
+        else dgamma[c] = (float)(2.0 * (double)gamma_weight[c] * s);
     }
 }
 
@@ -531,7 +542,7 @@ int launch_c0_bwd(const float *x, const float *w, const float *bias, const float
     conv0_gdn_kernel<C, true><<<grid, kC0Threads, C0Cfg<C, true>::SMEM, st>>>(x, w, bias, beta_param, gamma_weight, g, nullptr, nullptr, gy,
                                                                              part_dw, part_sums);
     SIC_CHECK_LAUNCH("sic_conv0_gdn_bwd");
-    const int n_out = C * kC0K + 3 * C;
+    const int n_out = C * (kC0K + 1) + 2 * C;
     conv0_gdn_bwd_finalize_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(part_dw, part_sums, grid, C, beta_param, gamma_weight, dw, dbias, dbeta,
                                                                      dgamma);
     SIC_CHECK_LAUNCH("sic_conv0_gdn_bwd (finalize)");

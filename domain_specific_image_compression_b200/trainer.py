@@ -101,6 +101,7 @@ class FlatTrainer:
         self._pending = [0] * len(self.buckets)
         self._works = []
         self._armed = False
+        self._main_stream = None
         self.fire_order: List[int] = []        # bucket indices in the order their all-reduce was issued in the last step
         for p in self.live:
             p.register_post_accumulate_grad_hook(self._on_grad)
@@ -117,9 +118,14 @@ class FlatTrainer:
     def _fire(self, k: int) -> None:
         """Every gradient of bucket k exists: pack them into the bucket's slice of the flat buffer and start its all-reduce."""
         lo, hi, a, b = self.buckets[k]
-        if self.flat_grad.is_cuda:             # gradients of one bucket may come from the model's side stream (model.OVERLAP_HYPER_BRANCH)
-            from .model import join_side_streams
-            join_side_streams(self.flat_grad.device)
+        if self.flat_grad.is_cuda:
+            # The gradients of one bucket may have been produced on the step's own stream or on the model's side stream
+            # (model.OVERLAP_HYPER_BRANCH), and this hook runs on whichever of the two produced the last one: wait for both.
+            from .model import _side_streams
+            cur = torch.cuda.current_stream(self.flat_grad.device)
+            for st in (self._main_stream, _side_streams.get(self.flat_grad.device.index)):
+                if st is not None and st != cur:
+                    cur.wait_stream(st)
         torch.cat([_flat_in_param_order(self.live[i].grad, self.live[i]) for i in range(a, b)], out=self.flat_grad[lo:hi])
         self.fire_order.append(k)
         if self.world > 1:                     # asynchronous: runs on the collective's own stream under the rest of backward()
@@ -155,6 +161,7 @@ class FlatTrainer:
         for k, (_, _, a, b) in enumerate(self.buckets):
             self._pending[k] = b - a
         self._works, self.fire_order, self._armed = [], [], True
+        self._main_stream = torch.cuda.current_stream(self.flat_grad.device) if self.flat_grad.is_cuda else None
         try:
             loss = loss_closure()
             loss.backward()
