@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--nchw", action="store_true", help="keep activations NCHW (default: torch.channels_last, which saves cuDNN's "
                     "internal NCHW<->NHWC transposes; GDN kernels run natively in either layout)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="cuDNN autotune is on by default (warm-up steps absorb it)")
+    ap.add_argument("--cudnn-benchmark-limit", type=int, default=-1, help="torch.backends.cudnn.benchmark_limit (PyTorch default 10 "
+                    "candidates per convolution; 0 = try every engine configuration cuDNN's heuristics return); -1 leaves it alone")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying one CUDA graph")
     ap.add_argument("--no-fuse-first-layer", action="store_true", help="keep g_a's first layer as cuDNN conv + GDN kernel (default: the fused "
                     "conv 3->N 3x3 + bias + GDN tcgen05 kernel, forward and backward: layers.FUSE_FIRST_LAYER)")
@@ -238,6 +240,8 @@ def run_ours(args):
     fused_first = not (args.no_fuse_first_layer or args.pad_rgb or args.gdn == "dense" or args.nchw)
     roof, kernels = kernel_rooflines(cfg, dev, channels_last=not args.nchw, fused_first_layer=fused_first) if rank == 0 else (None, None)
     torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
+    if args.cudnn_benchmark_limit >= 0:
+        torch.backends.cudnn.benchmark_limit = args.cudnn_benchmark_limit
     gpu_eager = None
     if rank == 0 and world == 1 and not args.no_gpu_eager_baseline:
         try:
@@ -326,9 +330,14 @@ def run_ours(args):
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
+            allms = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(allms, ms)
+            per_rank_ms.clear()
+            per_rank_ms.extend(float(v) / steps for v in allms)
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    per_rank_ms = []
     W_, K = max(3, args.warmup), max(1, args.steps)
     for _ in range(W_):
         step_resident()
@@ -385,11 +394,11 @@ def run_ours(args):
                        "activation_layout": "NCHW" if args.nchw else "channels_last", "launch": graph_note,
                        "rgb_channel_padding": args.pad_rgb, "gdn": args.gdn, "fused_first_layer": bool(_layers.FUSE_FIRST_LAYER), "gemm_last_layer": bool(_layers.FAST_LAST_LAYER), "hyper_branch_on_side_stream": bool(_model.OVERLAP_HYPER_BRANCH),
                        "gradient_buckets": [hi - lo for lo, hi, _, _ in trainer.buckets] if world > 1 else None,
-                       "cudnn_benchmark": not args.no_cudnn_benchmark},
+                       "cudnn_benchmark": not args.no_cudnn_benchmark, "cudnn_benchmark_limit": torch.backends.cudnn.benchmark_limit},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / K, "last_loss": e2e_losses[-1],
                     "how": "HostFedLoop: pinned batch -> copy stream -> landing buffer -> static input; loss -> pinned host, read one step late"},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base,
+            "gpu_launches": launches, "per_rank_ms_per_step": per_rank_ms or None, "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base,
             "gpu_eager_baseline": gpu_eager,
             "allreduce_bytes_per_step": trainer.nbytes_allreduce if world > 1 else 0,
         }

@@ -548,7 +548,52 @@ __global__ void __launch_bounds__(kThreads, MODE == MODE_T_BCAST ? 4 : 3) bottle
             o_dm = -gx;
         };
 
-        if (VEC) {
+        if (MODE == MODE_T_BCAST && VEC && g_nll == nullptr && mu == nullptr && dmu == nullptr) {
+            // The training call: the loss reaches the likelihood only through the per-patch bit counts (g_bits), there is no mu and
+            // sigma / nu are per row.  Then the upstream gradient gt = g_bits[b] is a row constant: it is factored out of the three
+            // sums (applied once per lane below) and folded into the dy coefficient; no dmu work at all.  r02o: the generic loop
+            // costs 45 instructions per element (126 M warp instructions, 66 % issue utilisation, 80 % of HBM); this one 13.
+            constexpr int U = 2;
+            const int v0 = e0 >> 2, v1 = e1 >> 2;
+            const long vbase = base >> 2;
+            const bool has_gy = g_yt != nullptr && pass_dy;
+            const float cdx = pass_dy ? kLog2e * gb : 0.0f;          // dy = gy + gt * log2e * (nu+1) x / (nu sigma^2 + x^2)
+            float cnt = 0.f;
+            auto elem = [&](float x, float gyv, float &o) {
+                const float q = x * x;
+                const float t = tc.np1 * __fdividef(1.0f, tc.sigma2nu + q);
+                acc_s += 1.0f - t * q;
+                acc_n += __log2f(fmaf(q, tc.inv_sigma2nu, 1.0f));
+                o = fmaf(cdx * t, x, gyv);
+            };
+            for (int v = v0 + lane; v < v1; v += 32 * U) {
+                float4 a[U], gy[U];
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const int vv = v + 32 * k;
+                    if (vv < v1) {
+                        a[k] = ldg_stream(reinterpret_cast<const float4 *>(yt) + vbase + vv);
+                        gy[k] = has_gy ? ldg_stream(reinterpret_cast<const float4 *>(g_yt) + vbase + vv) : make_float4(0, 0, 0, 0);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < U; ++k) {
+                    const int vv = v + 32 * k;
+                    if (vv < v1) {
+                        float4 o;
+                        elem(a[k].x, gy[k].x, o.x);
+                        elem(a[k].y, gy[k].y, o.y);
+                        elem(a[k].z, gy[k].z, o.z);
+                        elem(a[k].w, gy[k].w, o.w);
+                        cnt += 4.0f;
+                        if (dy) stg_stream(reinterpret_cast<float4 *>(dy) + vbase + vv, o);
+                    }
+                }
+            }
+            acc_s *= gb;            // sum gt (1 - rq)
+            acc_n *= gb;            // sum gt log2(1 + u)
+            acc_0 = gb * cnt;       // sum gt
+        } else if (VEC) {
             constexpr int U = is_spatial(MODE) ? 1 : 2;
             const int v0 = e0 >> 2, v1 = e1 >> 2;
             const long vbase = base >> 2;

@@ -25,6 +25,11 @@ import torch
 import torch.distributed as dist
 
 
+# SIC_DIAG_NO_ALLREDUCE=1: timing diagnosis only (how much of a multi-GPU step is the collective?) - replicas diverge, never train so
+import os as _os
+_DIAG_NO_ALLREDUCE = bool(_os.environ.get("SIC_DIAG_NO_ALLREDUCE"))
+
+
 def _dead_parameter_names(module: torch.nn.Module) -> set:
     """Parameters that never receive a gradient, decided per GDN site: the diagonal path (the reference's, layers.py:21) uses
     `gamma_conv.weight` and leaves the stored CxC `gamma` (layers.py:13) untouched; GDN(dense=True) is the other way round."""
@@ -128,7 +133,7 @@ class FlatTrainer:
                     cur.wait_stream(st)
         torch.cat([_flat_in_param_order(self.live[i].grad, self.live[i]) for i in range(a, b)], out=self.flat_grad[lo:hi])
         self.fire_order.append(k)
-        if self.world > 1:                     # asynchronous: runs on the collective's own stream under the rest of backward()
+        if self.world > 1 and not _DIAG_NO_ALLREDUCE:   # asynchronous: runs on the collective's own stream under the rest of backward()
             self._works.append(dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def pack_grads(self) -> torch.Tensor:
