@@ -54,6 +54,8 @@ PROTOTYPES = {
     "sic_hyper_tail_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, ctypes.c_float, ctypes.c_float] + [_p] * 11),
     "sic_ssim_tiles": (_l, [_i, _i]),
     "sic_ssim_fwd": (_i, [_p, _p, _i, _i, _i, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p]),
+    "sic_ssim_fwd_pool": (_i, [_p, _p, _i, _i, _i, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p, _p, _p]),
+    "sic_ssim_bwd_pool": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "sic_ssim_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "sic_quantize_indices": (_i, [_p, _i, _l, _i, _i, _p, _p, _p, _p]),
     "sic_build_cdf_tables": (_i, [_i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p]),

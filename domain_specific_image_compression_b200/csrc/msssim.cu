@@ -30,7 +30,8 @@ __constant__ float c_g[kK] = {1.028380357e-03f, 7.598758209e-03f, 3.600077331e-0
 // maps (nullable): [5][planes][Hv][Wv] = M2mu, M2xx, M2xy, l, T   (see ssim_bwd_kernel)
 __global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(const float *__restrict__ X, const float *__restrict__ Y, int H, int W,
                                                             float c1, float c2, float *__restrict__ part_ss,
-                                                            float *__restrict__ part_cs, float *__restrict__ maps, long map_stride) {
+                                                            float *__restrict__ part_cs, float *__restrict__ maps, long map_stride,
+                                                            float *__restrict__ x_pool, float *__restrict__ y_pool) {
     __shared__ float sx[kHalo][kHalo + 1], sy[kHalo][kHalo + 1];
     __shared__ float hb[5][kHalo][kT + 1];
     __shared__ float red[2][kThreads / 32];
@@ -46,6 +47,19 @@ __global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(const float *__restr
         sy[r][c] = in ? __ldg(yp + (long)gy * W + gx) : 0.f;
     }
     __syncthreads();
+    if (x_pool != nullptr) {
+        // next scale's inputs as a by-product (2x2 average pooling, losses.py / piq): this CTA owns the input rows / columns
+        // [32 by, 32 by + 32) of its 42-wide halo tile, the last tile of each axis everything up to the image edge (<= 42: the
+        // halo always reaches it).  H and W are even here (the host keeps the torch pooling for odd sizes).
+        const int Hp = H >> 1, Wp = W >> 1;
+        const int rows = (blockIdx.y == gridDim.y - 1 ? H - oy0 : kT) >> 1, cols = (blockIdx.x == gridDim.x - 1 ? W - ox0 : kT) >> 1;
+        for (int i = threadIdx.x; i < rows * cols; i += kThreads) {
+            const int pr = i / cols, pc = i - pr * cols;
+            const long o = (long)plane * Hp * Wp + (long)((oy0 >> 1) + pr) * Wp + ((ox0 >> 1) + pc);
+            x_pool[o] = 0.25f * ((sx[2 * pr][2 * pc] + sx[2 * pr][2 * pc + 1]) + (sx[2 * pr + 1][2 * pc] + sx[2 * pr + 1][2 * pc + 1]));
+            y_pool[o] = 0.25f * ((sy[2 * pr][2 * pc] + sy[2 * pr][2 * pc + 1]) + (sy[2 * pr + 1][2 * pc] + sy[2 * pr + 1][2 * pc + 1]));
+        }
+    }
     for (int i = threadIdx.x; i < kHalo * kT; i += kThreads) {   // horizontal pass
         int r = i / kT, c = i - r * kT;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
@@ -114,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(const float *__restr
 __global__ void __launch_bounds__(kThreads) ssim_bwd_kernel(const float *__restrict__ X, const float *__restrict__ Y,
                                                             const float *__restrict__ maps, long map_stride,
                                                             const float *__restrict__ g_ss, const float *__restrict__ g_cs, int H, int W,
-                                                            float *__restrict__ dX) {
+                                                            const float *__restrict__ g_pool, float *__restrict__ dX) {
     __shared__ float sm[3][kHalo][kHalo + 1];
     __shared__ float hb[3][kHalo][kT + 1];
     const int plane = blockIdx.z;
@@ -166,7 +180,10 @@ __global__ void __launch_bounds__(kThreads) ssim_bwd_kernel(const float *__restr
                 b2 = fmaf(g, hb[2][rr][c], b2);
             }
             long o = (long)plane * H * W + (long)qy * W + qx;
-            dX[o] = b0 + 2.f * __ldg(X + o) * b1 + __ldg(Y + o) * b2;
+            float d = b0 + 2.f * __ldg(X + o) * b1 + __ldg(Y + o) * b2;
+            // the gradient that arrives through the pooled copy of X (the coarser scales): avg_pool2d backward, 1/4 to each of the four
+            if (g_pool != nullptr) d = fmaf(0.25f, __ldg(g_pool + (long)plane * (H >> 1) * (W >> 1) + (long)(qy >> 1) * (W >> 1) + (qx >> 1)), d);
+            dX[o] = d;
         }
     }
 }
@@ -183,28 +200,41 @@ extern "C" long sic_ssim_tiles(int H, int W) {
     return (long)((H - 10 + kT - 1) / kT) * ((W - 10 + kT - 1) / kT);
 }
 
-extern "C" int sic_ssim_fwd(const float *X, const float *Y, int planes, int H, int W, float c1, float c2, float *part_ss,
-                            float *part_cs, float *maps, void *stream) {
+extern "C" int sic_ssim_fwd_pool(const float *X, const float *Y, int planes, int H, int W, float c1, float c2, float *part_ss,
+                                 float *part_cs, float *maps, float *x_pool, float *y_pool, void *stream) {
     SIC_CHECK_ARG(planes > 0 && H >= 11 && W >= 11, "sic_ssim_fwd: needs planes > 0 and images of at least 11x11 (got %d, %dx%d)", planes, H, W);
     SIC_CHECK_ARG(X && Y && part_ss && part_cs, "sic_ssim_fwd: null pointer");
     SIC_CHECK_ARG(planes <= 65535, "sic_ssim_fwd: more than 65535 (batch x channel) planes");
+    SIC_CHECK_ARG((x_pool == nullptr) == (y_pool == nullptr), "sic_ssim_fwd_pool: x_pool and y_pool go together");
+    SIC_CHECK_ARG(x_pool == nullptr || ((H | W) & 1) == 0, "sic_ssim_fwd_pool: pooled outputs need even H and W (got %dx%d)", H, W);
     cudaStream_t st = (cudaStream_t)stream;
     const int Hv = H - 10, Wv = W - 10;
     dim3 grid((Wv + kT - 1) / kT, (Hv + kT - 1) / kT, planes);
-    ssim_fwd_kernel<<<grid, kThreads, 0, st>>>(X, Y, H, W, c1, c2, part_ss, part_cs, maps, (long)planes * Hv * Wv);
+    ssim_fwd_kernel<<<grid, kThreads, 0, st>>>(X, Y, H, W, c1, c2, part_ss, part_cs, maps, (long)planes * Hv * Wv, x_pool, y_pool);
     SIC_CHECK_LAUNCH("sic_ssim_fwd");
+    return 0;
+}
+
+extern "C" int sic_ssim_fwd(const float *X, const float *Y, int planes, int H, int W, float c1, float c2, float *part_ss,
+                            float *part_cs, float *maps, void *stream) {
+    return sic_ssim_fwd_pool(X, Y, planes, H, W, c1, c2, part_ss, part_cs, maps, nullptr, nullptr, stream);
+}
+
+extern "C" int sic_ssim_bwd_pool(const float *X, const float *Y, const float *maps, const float *g_ss, const float *g_cs,
+                                 const float *g_pool, int planes, int H, int W, float *dX, void *stream) {
+    SIC_CHECK_ARG(planes > 0 && H >= 11 && W >= 11, "sic_ssim_bwd: bad extents");
+    SIC_CHECK_ARG(X && Y && maps && dX, "sic_ssim_bwd: null pointer");
+    SIC_CHECK_ARG(planes <= 65535, "sic_ssim_bwd: more than 65535 (batch x channel) planes");
+    SIC_CHECK_ARG(g_pool == nullptr || ((H | W) & 1) == 0, "sic_ssim_bwd_pool: a pooled gradient needs even H and W (got %dx%d)", H, W);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Hv = H - 10, Wv = W - 10;
+    dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, planes);
+    ssim_bwd_kernel<<<grid, kThreads, 0, st>>>(X, Y, maps, (long)planes * Hv * Wv, g_ss, g_cs, H, W, g_pool, dX);
+    SIC_CHECK_LAUNCH("sic_ssim_bwd");
     return 0;
 }
 
 extern "C" int sic_ssim_bwd(const float *X, const float *Y, const float *maps, const float *g_ss, const float *g_cs, int planes,
                             int H, int W, float *dX, void *stream) {
-    SIC_CHECK_ARG(planes > 0 && H >= 11 && W >= 11, "sic_ssim_bwd: bad extents");
-    SIC_CHECK_ARG(X && Y && maps && dX, "sic_ssim_bwd: null pointer");
-    SIC_CHECK_ARG(planes <= 65535, "sic_ssim_bwd: more than 65535 (batch x channel) planes");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int Hv = H - 10, Wv = W - 10;
-    dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, planes);
-    ssim_bwd_kernel<<<grid, kThreads, 0, st>>>(X, Y, maps, (long)planes * Hv * Wv, g_ss, g_cs, H, W, dX);
-    SIC_CHECK_LAUNCH("sic_ssim_bwd");
-    return 0;
+    return sic_ssim_bwd_pool(X, Y, maps, g_ss, g_cs, nullptr, planes, H, W, dX, stream);
 }

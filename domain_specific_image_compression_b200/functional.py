@@ -194,12 +194,30 @@ def quantize(x: torch.Tensor, mode: str) -> torch.Tensor:
     x = _require_cuda_f32(x, "x")
     if x.numel() == 0:
         return x
-    flat = x.reshape(1, 1, -1)
-    zero = _zeros1.get(x.device)
-    if zero is None:
-        zero = _zeros1[x.device] = torch.zeros(1, dtype=torch.float32, device=x.device)
-    y_tilde, _, _ = bottleneck(flat, zero, quant=mode, lik="gaussian", want_nll=False)
-    return y_tilde.view(x.shape)
+    return _Quantize.apply(x, mode)
+
+
+class _Quantize(torch.autograd.Function):
+    """Quantise-only form of K1.  The backward is the identity ('noise') or zero ('round', like torch.round): no kernel.  (Routing
+    it through the likelihood kernel's backward cost 134 us per step in the overlapped schedule: with one row of 786 k elements the
+    per-channel fold of that kernel's partials is a single thread's loop, r02v launch list.)"""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, x, mode: str):
+        flat = x.reshape(1, 1, -1)
+        zero = _zeros1.get(x.device)
+        if zero is None:
+            zero = _zeros1[x.device] = torch.zeros(1, dtype=torch.float32, device=x.device)
+        with torch.no_grad():
+            y_tilde, _, _ = bottleneck(flat, zero, quant=mode, lik="gaussian", want_nll=False)
+        ctx.mode = mode
+        return y_tilde.view(x.shape)
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g):
+        return (g if ctx.mode == "noise" else torch.zeros_like(g)), None
 
 
 _zeros1 = {}
@@ -522,7 +540,7 @@ def hyper_tail(t: torch.Tensor, mlp_sigma, mlp_nu, min_nu: float, max_nu: float)
 class _SSIMStats(torch.autograd.Function):
     @staticmethod
     @_amp_fwd
-    def forward(ctx, x, y, c1: float, c2: float):
+    def forward(ctx, x, y, c1: float, c2: float, want_pool: bool):
         lib = _lib.load()
         x = _require_cuda_f32(x, "x")
         y = _require_cuda_f32(y, "y")
@@ -531,38 +549,48 @@ class _SSIMStats(torch.autograd.Function):
         B, C, H, W = x.shape
         if H < 11 or W < 11:
             raise ValueError("Kernel size can't be greater than actual input size.")
+        if want_pool and ((H | W) & 1):
+            raise _lib.SicError("ssim_stats: pooled outputs need even H and W")
         planes, tiles = B * C, lib.sic_ssim_tiles(H, W)
         part = torch.empty((2, planes, tiles), dtype=torch.float32, device=x.device)
         need = ctx.needs_input_grad[0]
         maps = torch.empty((5, planes, H - 10, W - 10), dtype=torch.float32, device=x.device) if need else None
+        xp = torch.empty((B, C, H // 2, W // 2), dtype=torch.float32, device=x.device) if want_pool else None
+        yp = torch.empty_like(xp) if want_pool else None
         with torch.cuda.device(x.device):
-            _launch(lib.sic_ssim_fwd(_ptr(x), _ptr(y), planes, H, W, c1, c2, _ptr(part[0]), _ptr(part[1]), _ptr(maps), _stream()),
-                    "sic_ssim_fwd")
+            _launch(lib.sic_ssim_fwd_pool(_ptr(x), _ptr(y), planes, H, W, c1, c2, _ptr(part[0]), _ptr(part[1]), _ptr(maps), _ptr(xp), _ptr(yp),
+                                          _stream()), "sic_ssim_fwd")
         means = part.sum(dim=2) * (1.0 / ((H - 10) * (W - 10)))             # fixed-order fold of the per-tile partials
         if need:
             ctx.save_for_backward(x, y, maps)
         ctx.set_materialize_grads(False)
-        return means[0].view(B, C), means[1].view(B, C)
+        if want_pool:
+            ctx.mark_non_differentiable(yp)
+        return means[0].view(B, C), means[1].view(B, C), xp, yp
 
     @staticmethod
     @_amp_bwd
-    def backward(ctx, g_ss, g_cs):
+    def backward(ctx, g_ss, g_cs, g_xp, _g_yp):
         lib = _lib.load()
         x, y, maps = ctx.saved_tensors
         B, C, H, W = x.shape
         g_ss = None if g_ss is None else _require_cuda_f32(g_ss, "g_ss")
         g_cs = None if g_cs is None else _require_cuda_f32(g_cs, "g_cs")
+        g_xp = None if g_xp is None else _require_cuda_f32(g_xp, "g_x_pool")
         dx = torch.empty_like(x)
         with torch.cuda.device(x.device):
-            _launch(lib.sic_ssim_bwd(_ptr(x), _ptr(y), _ptr(maps), _ptr(g_ss), _ptr(g_cs), B * C, H, W, _ptr(dx), _stream()),
+            _launch(lib.sic_ssim_bwd_pool(_ptr(x), _ptr(y), _ptr(maps), _ptr(g_ss), _ptr(g_cs), _ptr(g_xp), B * C, H, W, _ptr(dx), _stream()),
                     "sic_ssim_bwd")
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
-def ssim_stats(x: torch.Tensor, y: torch.Tensor, c1: float = 0.01 ** 2, c2: float = 0.03 ** 2):
+def ssim_stats(x: torch.Tensor, y: torch.Tensor, c1: float = 0.01 ** 2, c2: float = 0.03 ** 2, pool: bool = False):
     """Per-(batch, channel) means of the SSIM map and of its contrast-structure factor for one scale: (ss [B,C], cs [B,C]).
-    Differentiable w.r.t. x only (y is the target)."""
-    return _SSIMStats.apply(x, y, float(c1), float(c2))
+    Differentiable w.r.t. x only (y is the target).  pool=True (even H, W): also returns the next MS-SSIM scale's inputs, the 2x2
+    average-pooled x and y, written by the same kernel - (ss, cs, x_pool, y_pool); the gradient that later arrives at x_pool is added
+    inside this scale's backward kernel."""
+    ss, cs, xp, yp = _SSIMStats.apply(x, y, float(c1), float(c2), bool(pool))
+    return (ss, cs, xp, yp) if pool else (ss, cs)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -33,17 +33,32 @@ def multi_scale_ssim(x, y, data_range=1.0, scale_weights=None, kernel_size=11, k
     if y.requires_grad:
         raise _lib.SicError("multi_scale_ssim: differentiable w.r.t. the reconstruction only (the target must not require grad)")
     # float16 reconstructions arrive here under the reference's autocast training (train.py:196-199): computed in float32
-    x = x.float() / float(data_range)
-    y = y.float() / float(data_range)
+    x, y = x.float(), y.float()
+    if float(data_range) != 1.0:              # the reference calls with data_range = 1: no scaling pass (forward and backward) at all
+        x = x / float(data_range)
+        y = y / float(data_range)
     c1, c2 = k1 ** 2, k2 ** 2
     terms = []
     ssim_last = None
+    pooled = None
     for level in range(levels):
         if level > 0:
-            pad = max(x.shape[2] % 2, x.shape[3] % 2)
-            x = F.avg_pool2d(F.pad(x, [pad, 0, pad, 0], mode="replicate"), kernel_size=2, padding=0)
-            y = F.avg_pool2d(F.pad(y, [pad, 0, pad, 0], mode="replicate"), kernel_size=2, padding=0)
-        ssim_last, cs = F_sic.ssim_stats(x, y, c1, c2)       # one fused kernel per scale; raises on CPU tensors
+            if pooled is not None:            # written by the previous scale's kernel (even sizes)
+                x, y = pooled
+            else:
+                pad = max(x.shape[2] % 2, x.shape[3] % 2)
+                if pad:                       # odd sizes: replicate-pad top/left, then pool, in torch
+                    x = F.pad(x, [pad, 0, pad, 0], mode="replicate")
+                    y = F.pad(y, [pad, 0, pad, 0], mode="replicate")
+                x = F.avg_pool2d(x, kernel_size=2, padding=0)
+                y = F.avg_pool2d(y, kernel_size=2, padding=0)
+        fuse_pool = level + 1 < levels and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0
+        if fuse_pool:                         # one kernel: this scale's statistics + the next scale's inputs
+            ssim_last, cs, xp, yp = F_sic.ssim_stats(x, y, c1, c2, pool=True)
+            pooled = (xp, yp)
+        else:
+            ssim_last, cs = F_sic.ssim_stats(x, y, c1, c2)       # raises on CPU tensors
+            pooled = None
         terms.append(cs)
     stacked = torch.relu(torch.stack(terms[:-1] + [ssim_last], dim=0))          # [levels,B,C]
     powered = stacked ** scale_weights.view(-1, 1, 1)

@@ -224,6 +224,14 @@ int sic_build_cdf_tables(int kind, const float *sigma, const float *nu, int n_ro
  *   fwd: part_ss / part_cs [planes * sic_ssim_tiles(H,W)] per-tile sums of the ss and cs maps over the valid region (the host
  *        folds them and divides by (H-10)(W-10)); maps (nullable) [5, planes, H-10, W-10]: what bwd needs.
  *   bwd: dX = d(g_ss[plane]*mean(ss) + g_cs[plane]*mean(cs))/dX ; g_ss / g_cs [planes], either may be NULL (= 0). */
+/* The same two kernels with the 2x2 average pooling between MS-SSIM scales folded in (even H and W): the forward also writes the next
+ * scale's inputs x_pool / y_pool [planes, H/2, W/2] (nullable pair), the backward adds the gradient that arrives through that pooled
+ * copy (g_pool [planes, H/2, W/2], nullable; avg_pool2d backward = 1/4 to each of the four pixels).  Replaces two avg_pool2d and one
+ * avg_pool2d_backward + add per scale boundary. */
+int sic_ssim_fwd_pool(const float *X, const float *Y, int planes, int H, int W, float c1, float c2, float *part_ss, float *part_cs,
+                      float *maps, float *x_pool, float *y_pool, void *stream);
+int sic_ssim_bwd_pool(const float *X, const float *Y, const float *maps, const float *g_ss, const float *g_cs, const float *g_pool,
+                      int planes, int H, int W, float *dX, void *stream);
 long sic_ssim_tiles(int H, int W);
 int sic_ssim_fwd(const float *X, const float *Y, int planes, int H, int W, float c1, float c2, float *part_ss, float *part_cs,
                  float *maps, void *stream);

@@ -40,7 +40,9 @@ if which in ("both", "ours"):
     from domain_specific_image_compression_b200 import layers as _L
     _L.FUSE_FIRST_LAYER = bool(os.environ.get("FUSE_FIRST", "1") != "0" and os.environ.get("CHANNELS_LAST"))
     _L.FAST_LAST_LAYER = bool(os.environ.get("FAST_LAST", "1") != "0" and os.environ.get("CHANNELS_LAST"))
-    print("fused first layer", _L.FUSE_FIRST_LAYER, "gemm last layer", _L.FAST_LAST_LAYER)
+    from domain_specific_image_compression_b200 import model as _M
+    _M.OVERLAP_HYPER_BRANCH = bool(os.environ.get("OVERLAP", "1") != "0" and os.environ.get("CHANNELS_LAST"))
+    print("fused first layer", _L.FUSE_FIRST_LAYER, "gemm last layer", _L.FAST_LAST_LAYER, "hyper branch on side stream", _M.OVERLAP_HYPER_BRANCH)
     tr = FlatTrainer(model)
     def closure():
         out = model(x, "noise"); return sic.rate_distortion_loss(out, x, 10000.0, "msssim")[0]

@@ -378,3 +378,38 @@ def test_dense_dgamma_kernel_vs_float64(C, P):
     big = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
     assert lib.sic_gdn_dense_dgamma(vp(x), vp(h), P, 48, vp(out), vp(big), big.numel(), None) == -3     # SIC_E_UNSUPPORTED
     assert lib.sic_gdn_dense_dgamma(vp(x), vp(h), P, C, vp(out), vp(ws), 0, None) == -2                 # SIC_E_WORKSPACE
+
+
+@pytest.mark.parametrize("channels_last", [0, 1])
+def test_backward_halves_equal_the_whole(channels_last):
+    """sic_gdn_bwd = sic_gdn_bwd_partials (streaming kernel) + sic_gdn_bwd_fold (fixed-order fold): calling the halves through the C
+    ABI gives the same bits as the combined entry point (bench.py times the streaming kernel on its own through the first half)."""
+    import ctypes
+    from domain_specific_image_compression_b200 import _lib
+    lib = _lib.load()
+    B, C, H, W = 3, 64, 24, 20
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    x = torch.randn(B, C, H, W, device="cuda", generator=gen).contiguous(memory_format=fmt)
+    g = torch.randn(B, C, H, W, device="cuda", generator=gen).contiguous(memory_format=fmt)
+    beta = torch.sqrt(torch.rand(C, device="cuda", generator=gen) + 0.5)
+    w = torch.sqrt(torch.rand(C, device="cuda", generator=gen) * 0.3 + 0.01)
+    bias = torch.randn(C, device="cuda", generator=gen) * 0.1
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nws = lib.sic_gdn_bwd_workspace_bytes(B, C, H * W)
+    res = []
+    for split in (False, True):
+        ws = torch.empty(max(nws, 16), dtype=torch.uint8, device="cuda")
+        dx = torch.full_like(x, float("nan"))
+        db, dg, dbi = (torch.full((C,), float("nan"), device="cuda") for _ in range(3))
+        if split:
+            assert lib.sic_gdn_bwd_partials(vp(x), vp(bias), vp(g), vp(beta), vp(w), B, C, H * W, 0, channels_last, vp(dx), vp(ws), ws.numel(), st) == 0
+            assert lib.sic_gdn_bwd_fold(vp(beta), vp(w), B, C, H * W, channels_last, vp(dbi), vp(db), vp(dg), vp(ws), ws.numel(), st) == 0
+        else:
+            assert lib.sic_gdn_bwd(vp(x), vp(bias), vp(g), vp(beta), vp(w), B, C, H * W, 0, channels_last, vp(dx), vp(dbi), vp(db), vp(dg),
+                                   vp(ws), ws.numel(), st) == 0, lib.sic_last_error()
+        res.append((dx, db, dg, dbi))
+    for a, b in zip(*res):
+        assert torch.equal(a, b) and torch.isfinite(a).all()
+    assert lib.sic_gdn_bwd_fold(vp(beta), vp(w), B, C, H * W, channels_last, vp(dbi), vp(db), vp(dg), vp(ws), 0, st) == -2      # SIC_E_WORKSPACE

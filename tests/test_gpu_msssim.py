@@ -62,6 +62,27 @@ def test_multi_scale_ssim_kernel_vs_oracle_chain():
     assert abs(float(c) - float(b)) < 2e-3
 
 
+@pytest.mark.parametrize("H,W", [(108, 84), (64, 64), (100, 76), (202, 44)])
+def test_fused_pooling_between_scales_vs_oracle_chain(H, W):
+    """Even sizes: the 2x2 average pooling between scales is written by the previous scale's forward kernel and its backward is added
+    inside that scale's backward kernel (sic_ssim_fwd_pool / sic_ssim_bwd_pool).  Value and gradient vs the oracle's conv2d +
+    avg_pool2d chain, at sizes that are not multiples of the 32-pixel tile (ragged last tiles own up to 42 rows / columns) and
+    that turn odd at a coarser scale (100x76 -> 50x38 -> 25x19)."""
+    F, losses = _mods()
+    g = torch.Generator(device="cuda").manual_seed(H + W)
+    y = torch.rand(2, 3, H, W, device="cuda", generator=g)
+    x0 = (y + 0.1 * torch.randn(2, 3, H, W, device="cuda", generator=g))
+    w = torch.tensor([0.3, 0.5, 0.2], device="cuda")
+    xa = x0.clone().requires_grad_(True)
+    va = losses.multi_scale_ssim(xa.clamp(0, 1), y, 1.0, w)
+    va.backward()
+    xb = x0.clone().requires_grad_(True)
+    vb = TP.multi_scale_ssim(xb.clamp(0, 1), y, 1.0, w)
+    vb.backward()
+    assert abs(float(va) - float(vb)) < 2e-6
+    assert float((xa.grad - xb.grad).abs().max()) <= 1e-4 * float(xb.grad.abs().max()) + 1e-10
+
+
 def test_no_cpu_path_for_the_loss():
     """north_star: no CPU fallback.  The distortion term raises on CPU tensors like every other op of the package."""
     import domain_specific_image_compression_b200 as sic
