@@ -13,12 +13,18 @@
 //                        tf32 operands, SW128_32B is the only available smem layout"): atoms of 4 K-rows x 128 B, the 32-byte chunk
 //                        index XORed with (row & 3), atoms LBO apart along M/N and SBO = 512 B apart along K.  (The first version
 //                        used the 16-byte SWIZZLE_128B pattern of the K-major kernels: the MMAs ran and returned zeros.)
-//   MMA warp             D[i, j] (TMEM, fp32, ONE accumulator that lives for the whole kernel) += hh*qh + hl*qh + hh*ql over K = 8
-//                        positions per instruction (a_major = b_major = MN in the instruction descriptor); the dropped hl*ql term is
-//                        2^-22 relative.  A plain tf32 product (truncating both operands) is biased by ~ -7e-4 relative, which
-//                        fails the 1e-4 gradient tolerance; the split costs tensor time only, and the pass is HBM-bound.
-//   end of kernel        TMEM -> per-CTA partial [C x C] in global memory; a second tiny kernel folds the <= 148 partials in a fixed
-//                        order (deterministic, no atomics).
+//   MMA warp             D[i, j] (TMEM, fp32) += hh*qh + hl*qh + hh*ql over K = 8 positions per instruction (a_major = b_major = MN in
+//                        the instruction descriptor); the dropped hl*ql term is 2^-22 relative.  A plain tf32 product (truncating
+//                        both operands) is biased by ~ -7e-4 relative, which fails the 1e-4 gradient tolerance; the split costs
+//                        tensor time only, and the pass is HBM-bound.
+//   flush warps (4)      The tensor core TRUNCATES when it adds into a large running sum: with ONE accumulator for the whole kernel
+//                        (first version) d(gamma) came out 1.35e-4 low at 10^6 positions (5e-8 per accumulating MMA, linear in the
+//                        position count; scripts/dgamma_bias_probe.py).  So an accumulator only lives for kDgFlushTiles = 16 tiles
+//                        (192 MMAs): then these warps read it (tcgen05.ld) and add it with round-to-nearest fp32 adds into the
+//                        per-CTA partial [C x C] in global memory (L2-resident; each element is owned by one thread: no atomics,
+//                        fixed order).  C <= 128: two accumulators alternate, so the MMAs never wait; C = 192 (no room for two):
+//                        the MMA warp waits for the read-out (~1 us per 16 tiles).
+//   afterwards           a second tiny kernel folds the <= 148 partials in a fixed order (deterministic).
 // C <= 128: one M = 128 block (rows >= C unused).  C == 192: M = 128 block (i = 0..127) + M = 64 block (i = 128..191, TMEM rows
 // 32*(r/16) + r%16 as in gdn_dense_ws.cu), N = 192 for both.
 #include "gdn_dense_ws.cuh"
@@ -29,8 +35,10 @@ namespace {
 using namespace umma;
 
 constexpr int kDgProdWarps = 8, kDgProdThreads = kDgProdWarps * 32;
-constexpr int kDgThreads = kDgProdThreads + 32;       // + the MMA warp
+constexpr int kDgFlushWarps = 4, kDgFlushThreads = kDgFlushWarps * 32;
+constexpr int kDgThreads = kDgProdThreads + 32 + kDgFlushThreads;   // producers, the MMA warp, the flush warps
 constexpr int kDgTN = 32;                             // positions (= K) per shared-memory stage
+constexpr int kDgFlushTiles = 16;                     // tiles per accumulator life (16 x 12 = 192 accumulating MMAs: bias <= 1e-5)
 
 template <int C>
 struct DgCfg {
@@ -45,7 +53,9 @@ struct DgCfg {
     static constexpr bool kTwoBlocks = C > 128;
     static constexpr int PER = kDgTN * (C / 4) / kDgProdThreads;      // float4 of h (and of x) per producer thread and stage
     static constexpr uint32_t COLS_B = 256;                           // TMEM column of the M = 64 block
-    static constexpr uint32_t TMEM_COLS = kTwoBlocks ? 512 : (C <= 32 ? 32 : C <= 64 ? 64 : 128);
+    static constexpr int NACC = kTwoBlocks ? 1 : 2;                   // accumulators that alternate between flush periods
+    static constexpr uint32_t ACC_STRIDE = 128;                       // TMEM columns between the two accumulators (C <= 128)
+    static constexpr uint32_t TMEM_COLS = kTwoBlocks ? 512 : 256;
     static_assert(C % 32 == 0 && (C <= 128 || C == 192), "C in {32,64,96,128,192}");
     static_assert((kDgTN * (C / 4)) % kDgProdThreads == 0 && NS >= 2, "stage geometry");
 };
@@ -83,16 +93,21 @@ __global__ void __launch_bounds__(kDgThreads, 1) gdn_dense_dgamma_kernel(const f
     constexpr uint32_t TILE = Cfg::TILE, LBO = TN * 128;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sStage = (smem_u32(smem_raw) + 1023u) & ~1023u;       // NS x { hh, hl, qh, ql }
-    __shared__ __align__(8) uint64_t bars[2 * NS + 1];                   // full[NS], empty[NS], done
+    __shared__ __align__(8) uint64_t bars[2 * NS + 4];                   // full[NS], empty[NS], acc_full[2], acc_free[2]
     __shared__ uint32_t tmem_base_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NS]), bar_done = smem_u32(&bars[2 * NS]);
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NS]);
+    const uint32_t bar_acc_full = smem_u32(&bars[2 * NS]), bar_acc_free = smem_u32(&bars[2 * NS + 2]);
+    constexpr int NACC = Cfg::NACC;
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
             mbar_init(bar_full + 8 * s, kDgProdThreads);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        mbar_init(bar_done, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_acc_full + 8 * a, 1);
+            mbar_init(bar_acc_free + 8 * a, kDgFlushThreads);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     if (warp == kDgProdWarps) {
@@ -105,6 +120,9 @@ __global__ void __launch_bounds__(kDgThreads, 1) gdn_dense_dgamma_kernel(const f
     const uint32_t tmem_base = tmem_base_slot;
     const long n_tiles = (P + TN - 1) / TN;
 
+    long n_local = 0;                                                    // tiles of this CTA, and its flush periods
+    for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_local;
+    const long n_periods = (n_local + kDgFlushTiles - 1) / kDgFlushTiles;
     if (warp < kDgProdWarps) {
         // ===================================================== producers: h, x -> (hh, hl, qh, ql) tiles
         float4 hn[PER], xn[PER];
@@ -153,13 +171,17 @@ __global__ void __launch_bounds__(kDgThreads, 1) gdn_dense_dgamma_kernel(const f
             request(tile + gridDim.x);
             prefetch(tile + 3 * (long)gridDim.x);
         }
-    } else {
+    } else if (warp == kDgProdWarps) {
         // ===================================================== MMA warp
         const uint32_t idescA = idesc_tf32_mn(128, C > 128 ? 192 : (C < 32 ? 32 : C)), idescB = idesc_tf32_mn(64, 192);
         uint32_t u = 0;
         for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++u) {
             const uint32_t s = u % NS, ph = (u / NS) & 1;
             const uint32_t sHH = sStage + s * Cfg::STAGE, sHL = sHH + TILE, sQH = sHL + TILE, sQL = sQH + TILE;
+            const uint32_t period = u / kDgFlushTiles, in_period = u % kDgFlushTiles, acc = period % NACC;
+            const uint32_t tmem_acc = tmem_base + acc * Cfg::ACC_STRIDE;
+            if (in_period == 0 && period >= (uint32_t)NACC)             // the flush warps have read this accumulator's previous life
+                mbar_wait(bar_acc_free + 8 * acc, ((period / NACC) - 1) & 1);
             mbar_wait(bar_full + 8 * s, ph);
             fence_after_sync();
             if (elect_one_sync()) {
@@ -169,46 +191,60 @@ __global__ void __launch_bounds__(kDgThreads, 1) gdn_dense_dgamma_kernel(const f
 #pragma unroll
                     for (int ks = 0; ks < TN / 8; ++ks) {                // 8 positions (two 4-row atoms, 1024 bytes) per instruction
                         const uint64_t dA = smem_desc_mn(sa + ks * 1024, LBO), dB = smem_desc_mn(sb + ks * 1024, LBO);
-                        const uint32_t accumulate = (u | (uint32_t)term | (uint32_t)ks) != 0;
-                        mma_tf32(tmem_base, dA, dB, idescA, accumulate);
+                        const uint32_t accumulate = (in_period | (uint32_t)term | (uint32_t)ks) != 0;   // fresh accumulator every period
+                        mma_tf32(tmem_acc, dA, dB, idescA, accumulate);
                         if (Cfg::kTwoBlocks)                             // rows i = 128..191: A starts four 32-channel atoms further on
-                            mma_tf32(tmem_base + Cfg::COLS_B, smem_desc_mn(sa + ks * 1024 + 4 * LBO, LBO), dB, idescB, accumulate);
+                            mma_tf32(tmem_acc + Cfg::COLS_B, smem_desc_mn(sa + ks * 1024 + 4 * LBO, LBO), dB, idescB, accumulate);
                     }
                 }
                 mma_commit(bar_empty + 8 * s);
-                if (tile + gridDim.x >= n_tiles) mma_commit(bar_done);   // last tile of this CTA: accumulator complete
+                if (in_period == kDgFlushTiles - 1 || tile + gridDim.x >= n_tiles) mma_commit(bar_acc_full + 8 * acc);   // period complete
             }
             __syncwarp();
         }
-    }
-    // ===================================================== read-out: TMEM -> partial[blockIdx.x][i][j]
-    if (warp < 4) {
-        mbar_wait(bar_done, 0);
-        fence_after_sync();
+    } else {
+        // ===================================================== flush warps: TMEM accumulator of one period -> += partial[blockIdx.x][i][j]
+        const int lq = warp & 3;                                         // TMEM lane quadrant = warp % 4 (warps 9..12 -> 1, 2, 3, 0)
         float *out = partial + (size_t)blockIdx.x * C * C;
-        const int iA = warp * 32 + lane;
-        if (warp * 32 < C && warp * 32 < 128) {
+        const int iA = lq * 32 + lane;
+        const int iB = 128 + lq * 16 + (lane & 15);
+        for (long p = 0; p < n_periods; ++p) {
+            const uint32_t acc = (uint32_t)(p % NACC);
+            const uint32_t tmem_acc = tmem_base + acc * Cfg::ACC_STRIDE;
+            mbar_wait(bar_acc_full + 8 * acc, (uint32_t)((p / NACC) & 1));
+            fence_after_sync();
+            if (lq * 32 < C && lq * 32 < 128) {
 #pragma unroll 1
-            for (int j0 = 0; j0 < C; j0 += 16) {
-                float acc[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)j0, acc);
+                for (int j0 = 0; j0 < C; j0 += 16) {
+                    float a16[16];
+                    tmem_ld16(tmem_acc + ((uint32_t)(lq * 32) << 16) + (uint32_t)j0, a16);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4 *>(out + (size_t)iA * C + j0 + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-            }
-        }
-        if (Cfg::kTwoBlocks) {
-            const int iB = 128 + warp * 16 + (lane & 15);
-#pragma unroll 1
-            for (int j0 = 0; j0 < C; j0 += 16) {
-                float acc[16];
-                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + Cfg::COLS_B + (uint32_t)j0, acc);   // warp-collective: all lanes load
-                if (lane < 16) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        *reinterpret_cast<float4 *>(out + (size_t)iB * C + j0 + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                        float4 *dst = reinterpret_cast<float4 *>(out + (size_t)iA * C + j0 + 4 * k4);
+                        float4 v = make_float4(a16[4 * k4], a16[4 * k4 + 1], a16[4 * k4 + 2], a16[4 * k4 + 3]);
+                        if (p > 0) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                        *dst = v;
+                    }
                 }
             }
+            if (Cfg::kTwoBlocks) {
+#pragma unroll 1
+                for (int j0 = 0; j0 < C; j0 += 16) {
+                    float a16[16];
+                    tmem_ld16(tmem_acc + ((uint32_t)(lq * 32) << 16) + Cfg::COLS_B + (uint32_t)j0, a16);   // warp-collective: all lanes load
+                    if (lane < 16) {
+#pragma unroll
+                        for (int k4 = 0; k4 < 4; ++k4) {
+                            float4 *dst = reinterpret_cast<float4 *>(out + (size_t)iB * C + j0 + 4 * k4);
+                            float4 v = make_float4(a16[4 * k4], a16[4 * k4 + 1], a16[4 * k4 + 2], a16[4 * k4 + 3]);
+                            if (p > 0) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                            *dst = v;
+                        }
+                    }
+                }
+            }
+            fence_before_sync();
+            mbar_arrive(bar_acc_free + 8 * acc);                         // this accumulator may start its next life
         }
     }
     fence_before_sync();
