@@ -96,12 +96,14 @@ class CompressionModel(nn.Module):
         nu_k = torch.clamp(torch.exp(log_nu).mean(dim=(2, 3), keepdim=True), self.min_nu, self.max_nu)
         return sigma_k, nu_k, sigma_k.expand_as(like), nu_k.expand_as(like)
 
-    def forward(self, x, quant_mode="noise", noise_y=None, noise_z=None):
-        """noise_y / noise_z (optional, not in the reference): supply the uniform draws for bit-exact parity runs."""
+    def forward(self, x, quant_mode="noise", noise_y=None, noise_z=None, synthesize=True):
+        """noise_y / noise_z (optional, not in the reference): supply the uniform draws for bit-exact parity runs.
+        synthesize=False (not in the reference; compress() uses it): stop after the entropy bottleneck - the same dict without
+        `x_hat`; the encoder needs latents, sigma and nu, not the reconstruction (g_s is ~40 % of a forward pass)."""
         if quant_mode not in ("noise", "round"):
             raise ValueError(f"Unknown quant mode: {quant_mode}")
         y = self.g_a(x)
-        if OVERLAP_HYPER_BRANCH and self.training and quant_mode == "noise" and y.is_cuda:
+        if OVERLAP_HYPER_BRANCH and self.training and quant_mode == "noise" and y.is_cuda and synthesize:
             return self._forward_overlapped(y, noise_y, noise_z)
         z = self.h_a(y)
         # K1 (Gaussian): quantise z + nll_z + per-patch bits in one launch (model.py:45,59)
@@ -114,9 +116,10 @@ class CompressionModel(nn.Module):
             y_hat = y_tilde                                                 # model.py:62
         else:
             y_hat = y_tilde if quant_mode == "round" else torch.round(y)   # round(y) twice in the reference; identical bits
-        x_hat = self.g_s(y_hat)
-        return {"x_hat": x_hat, "nll_y": nll_y, "nll_z": nll_z, "y": y, "y_tilde": y_tilde, "z": z, "z_tilde": z_tilde,
-                "sigma": sigma, "nu": nu}
+        out = {"nll_y": nll_y, "nll_z": nll_z, "y": y, "y_tilde": y_tilde, "z": z, "z_tilde": z_tilde, "sigma": sigma, "nu": nu}
+        if synthesize:
+            out = {"x_hat": self.g_s(y_hat), **out}
+        return out
 
     def _forward_overlapped(self, y, noise_y, noise_z):
         """Training forward with the hyperprior branch on a side stream (OVERLAP_HYPER_BRANCH).  Same nine outputs."""
@@ -153,7 +156,7 @@ class CompressionModel(nn.Module):
         self.eval()
         try:
             with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True):
-                out = self(x, quant_mode="round")
+                out = self(x, quant_mode="round", synthesize=False)    # the encoder does not need the reconstruction
         finally:
             self.train(was_training)
         y_q, z_q = out["y_tilde"], out["z_tilde"]
