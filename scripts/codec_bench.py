@@ -22,14 +22,19 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 16
 torch.manual_seed(42)
 m = sic.CompressionModel(N=128, M=192, min_nu=2.0).to(dev).eval()
 with torch.no_grad():
     m.g_a.g_a[14].weight.mul_(40.0); m.h_a.h_a[6].weight.mul_(40.0); m.h_s.mlp_nu[2].bias.add_(1.5)
+NCHW = "--nchw" in sys.argv
+if not NCHW:      # channels_last model and patches (as the training bench): cuDNN then runs without its NCHW<->NHWC conversion kernels,
+    m = m.to(memory_format=torch.channels_last)      # 2.3 of 10.3 ms of GPU time per compress() call in the NCHW profile (r02ag)
 x_all = bench.synthetic_batch(B * world, 512, 512, 7, dev)          # every rank holds the global batch; it codes its own patches
+if not NCHW:
+    x_all = x_all.contiguous(memory_format=torch.channels_last)
 idx = CP.patch_indices(B * world, rank, world)
-x = x_all[idx]
+x = x_all[idx] if NCHW else x_all[idx].contiguous(memory_format=torch.channels_last)
 
 
 def barrier():
@@ -51,7 +56,7 @@ def timed(fn, reps=5):
     return ts[len(ts) // 2], r
 
 
-res = {"n_gpus": world, "patches_per_gpu": B, "image": "512x512", "model": "N=128 M=192", "scaling": "weak",
+res = {"activation_layout": "NCHW" if "--nchw" in sys.argv else "channels_last", "n_gpus": world, "patches_per_gpu": B, "image": "512x512", "model": "N=128 M=192", "scaling": "weak",
        "sharding": "patch index modulo world size, no data-path collective (codec_parallel)"}
 with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=True):
     ref = m(x, "round")
