@@ -60,6 +60,8 @@ PROTOTYPES = {
     "sic_quantize_indices": (_i, [_p, _i, _l, _i, _i, _p, _p, _p, _p]),
     "sic_build_cdf_tables": (_i, [_i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p]),
     "sic_rans_encode": (_i, [_p, _p, _p, _i, _l, _l, _l, _i, _p, _l, _p, _p]),
+    "sic_rans_encode_workspace_bytes": (_z, [_i, _l]),
+    "sic_rans_encode_ws": (_i, [_p, _p, _p, _i, _l, _l, _l, _i, _p, _l, _p, _p, _z, _p]),
     "sic_rans_decode": (_i, [_p, _p, _p, _p, _i, _l, _l, _l, _i, _l, _p, _p, _p]),
     "sic_rans_encode_host": (_l, [_p, _l, _p, _i, _i, _l, _p, _l]),
     "sic_rans_decode_host": (_i, [_p, _l, _l, _p, _i, _i, _l, _p]),

@@ -676,9 +676,12 @@ def rans_encode_device(sym: torch.Tensor, tables: torch.Tensor, Ls: torch.Tensor
     cap = (128 + 2 * n + 3) // 4 * 4
     out = torch.empty((S, cap), dtype=torch.uint8, device=sym.device)
     nbytes = torch.empty(S, dtype=torch.int32, device=sym.device)
+    ws = _workspace(sym.device, lib.sic_rans_encode_workspace_bytes(S, n), "scratch")
     with torch.cuda.device(sym.device):
-        _launch(lib.sic_rans_encode(_ptr(sym), _ptr(tables), _ptr(Ls), S, n, int(sym_per_row), int(rows_per_stream), tables.shape[-1],
-                                    _ptr(out), cap, _ptr(nbytes), _stream()), "sic_rans_encode")
+        _lib.check(lib.sic_rans_encode_ws(_ptr(sym), _ptr(tables), _ptr(Ls), S, n, int(sym_per_row), int(rows_per_stream), tables.shape[-1],
+                                          _ptr(out), cap, _ptr(nbytes), _ptr(ws), ws.numel(), _stream()), "sic_rans_encode_ws")
+    global launch_count
+    launch_count += 2
     return out, nbytes
 
 

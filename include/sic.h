@@ -253,6 +253,13 @@ int sic_rans_decode_host(const uint8_t *in, long nbytes, long n, const uint16_t 
  *   stream's support); out [n_streams, cap] with cap >= 128 + 2n, cap % 4 == 0; out_nbytes [n_streams] (-1: symbol out of
  *   range or support L outside [1, min(4096, stride-1)]).  decode: status [n_streams] = 0, SIC_E_TRUNCATED, SIC_E_CORRUPT (final
  *   states / word count do not close) or SIC_E_BADARG (L outside [1, min(4096, stride-1)]).  All pointers are DEVICE pointers. */
+/* sic_rans_encode_ws: the same encoder in two phases - a whole-GPU pass that turns every symbol into its (start, width, reciprocal)
+ * triple, then the one-warp-per-stream state machine with the division replaced by a multiply (exact) - for the price of a workspace of
+ * sic_rans_encode_workspace_bytes(n_streams, n) bytes (8 per symbol, any content).  Identical bytes. */
+size_t sic_rans_encode_workspace_bytes(int n_streams, long n);
+int sic_rans_encode_ws(const int32_t *sym, const uint16_t *tables, const int32_t *Ls, int n_streams, long n, long sym_per_row,
+                       long rows_per_stream, int stride, uint8_t *out, long cap, int32_t *out_nbytes, void *workspace,
+                       size_t workspace_bytes, void *stream);
 int sic_rans_encode(const int32_t *sym, const uint16_t *tables, const int32_t *Ls, int n_streams, long n, long sym_per_row,
                     long rows_per_stream, int stride, uint8_t *out, long cap, int32_t *out_nbytes, void *stream);
 int sic_rans_decode(const uint8_t *in, const int32_t *nbytes, const uint16_t *tables, const int32_t *Ls, int n_streams, long n,

@@ -39,6 +39,20 @@ def test_device_coder_bytes_equal_host_and_oracle(S, C, hw, Ls):
     n = C * hw
     out, nbytes = F.rans_encode_device(torch.from_numpy(syms.reshape(S, n)).cuda(), torch.from_numpy(tabs.reshape(S * C, -1)).cuda(),
                                        torch.tensor(Ls, dtype=torch.int32).cuda(), hw, C)
+    # the single-kernel encoder (sic_rans_encode, no workspace) and the two-phase one (sic_rans_encode_ws, what rans_encode_device runs)
+    # must emit the same bytes
+    import ctypes
+    from domain_specific_image_compression_b200 import _lib
+    lib = _lib.load()
+    sym_d, tab_d = torch.from_numpy(syms.reshape(S, n)).cuda(), torch.from_numpy(tabs.reshape(S * C, -1)).cuda()
+    Ls_d = torch.tensor(Ls, dtype=torch.int32).cuda()
+    out1, nb1 = torch.zeros_like(out), torch.zeros_like(nbytes)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.sic_rans_encode(vp(sym_d), vp(tab_d), vp(Ls_d), S, n, hw, C, tab_d.shape[-1], vp(out1), out1.shape[1], vp(nb1),
+                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)) == 0, lib.sic_last_error()
+    assert torch.equal(nb1, nbytes)
+    for s in range(S):
+        assert torch.equal(out1[s, :int(nb1[s])], out[s, :int(nbytes[s])])
     out, nbytes = out.cpu().numpy(), nbytes.cpu().numpy()
     for s in range(S):
         ref = clib.rans_encode(syms[s], tabs[s][:, :Ls[s] + 1], Ls[s], hw)
