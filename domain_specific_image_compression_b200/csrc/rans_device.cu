@@ -156,14 +156,21 @@ __global__ void __launch_bounds__(kWarps * 32) rans_encode_prepared_kernel(const
     }
     const long iters = (n + 31) / 32;
     constexpr int U = 8;
-    for (long jb = iters; jb > 0; jb -= U) {
-        uint2 e[U];
+    uint2 nxt[U];
+    auto fetch = [&](long jb) {                                       // the U iterations jb-1 ... jb-U (descending)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const long i = (jb - 1 - u) * 32 + lane;
-            e[u] = make_uint2(0u, 0u);                                // hi == 0: no symbol here (r >= 65536 for every real symbol)
-            if (jb - 1 - u >= 0 && i < n) e[u] = __ldcs(pp + i);
+            nxt[u] = make_uint2(0u, 0u);                              // hi == 0: no symbol here (r >= 65536 for every real symbol)
+            if (jb - 1 - u >= 0 && i < n) nxt[u] = __ldcs(pp + i);
         }
+    };
+    fetch(iters);
+    for (long jb = iters; jb > 0; jb -= U) {
+        uint2 e[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) e[u] = nxt[u];
+        fetch(jb - U);                                                // the next batch's loads fly while this batch's states update
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (jb - 1 - u < 0) break;                                // warp-uniform
@@ -213,9 +220,11 @@ __global__ void __launch_bounds__(kWarps * 32) rans_decode_kernel(const uint8_t 
     // global load in (almost) every iteration; refilled with one coalesced read when fewer than 32 words are left in it
     constexpr int kWin = 256;
     __shared__ uint16_t swin_all[kWarps][kWin];
-    // slot -> symbol: a 64-entry bucket table per staged row (lut[b] = last symbol whose start is <= b << 10), then a short linear
-    // scan; the plain binary search was ~7 dependent shared-memory reads per symbol, this is ~2 for the peaked rows of a trained model
-    __shared__ uint16_t slut_all[kWarps][64];
+    // slot -> symbol: a 64-bucket table per staged row (lut[b] = last symbol whose start is <= b << 10; lut[64] = L - 1) brackets the
+    // answer in [lut[b], lut[b + 1]], then a binary search inside the bracket: 0-1 steps for the buckets of the distribution's body,
+    // <= 5 in the tails (a linear scan from lut[b] walked through up to 30 one-count tail symbols whenever ONE lane of the warp landed
+    // there: 149 instructions per iteration, r02ak); the plain binary search over the whole row was ~7 dependent shared-memory reads
+    __shared__ uint16_t slut_all[kWarps][66];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x * kWarps + warp;
     if (s >= n_streams) return;
@@ -251,12 +260,16 @@ __global__ void __launch_bounds__(kWarps * 32) rans_decode_kernel(const uint8_t 
     refill(0);
     const bool staged = sym_per_row % 32 == 0;   // then the 32 symbols of an iteration share one row
     const bool small = n < (1L << 31) && sym_per_row < (1L << 31);   // 32-bit index arithmetic (a 64-bit division is ~120 instructions)
-    long cur_row = -1;
+    long cur_row = -1, next_row = 0;
+    const long its_per_row = staged ? sym_per_row / 32 : 0;
+    long it_in_row = 0;
     const long iters = (n + 31) / 32;
     for (long j = 0; j < iters; ++j) {
         const long i = j * 32 + lane;
         if (staged) {
-            long r = small ? (long)((uint32_t)(j * 32) / (uint32_t)sym_per_row) : (j * 32) / sym_per_row;
+            if (it_in_row == its_per_row) { it_in_row = 0; ++next_row; }       // staged: every row spans sym_per_row / 32 whole iterations
+            ++it_in_row;
+            const long r = next_row;
             if (r != cur_row) {
                 __syncwarp();
                 const uint16_t *row = tab + r * stride;
@@ -272,6 +285,7 @@ __global__ void __launch_bounds__(kWarps * 32) rans_decode_kernel(const uint8_t 
                     }
                     slut_all[warp][b] = (uint16_t)lo;
                 }
+                if (lane == 0) slut_all[warp][64] = (uint16_t)(L - 1);
                 __syncwarp();
             }
         }
@@ -281,9 +295,13 @@ __global__ void __launch_bounds__(kWarps * 32) rans_decode_kernel(const uint8_t 
             uint32_t lo = 0, hi = L, c0, c1;
             if (staged) {
                 lo = slut_all[warp][slot >> 10];                      // srow[lo] <= (slot >> 10) << 10 <= slot
-                c1 = srow[lo + 1];
-                while (c1 <= slot) { ++lo; c1 = srow[lo + 1]; }      // ends at lo <= L - 1: srow[L] = 65536 > slot
+                hi = (uint32_t)slut_all[warp][(slot >> 10) + 1] + 1u;  // srow[hi] > ((slot >> 10) + 1) << 10 > slot  (srow[L] = 65536)
+                while (hi - lo > 1) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (srow[mid] <= slot) lo = mid; else hi = mid;
+                }
                 c0 = srow[lo];
+                c1 = srow[lo + 1];
             } else {
                 const uint16_t *row = tab + (small ? (long)((uint32_t)i / (uint32_t)sym_per_row) : i / sym_per_row) * stride;
                 while (hi - lo > 1) {
