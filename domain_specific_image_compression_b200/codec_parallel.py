@@ -96,6 +96,13 @@ def compress_sharded(model, x: torch.Tensor, tail: int = 10, coder: str = "gpu",
     return merge_compressed(parts, B)
 
 
+def gather_order(n_patches: int, world: int) -> List[int]:
+    """Where global patch i sits in the concatenation of the ranks' equal-sized blocks (each padded to ceil(B / W) patches):
+    rank r's j-th patch is global patch r + j * W, i.e. patch i is entry i // W of block i % W."""
+    per = (n_patches + world - 1) // world
+    return [(i % world) * per + i // world for i in range(n_patches)]
+
+
 def _is_nccl(group) -> bool:
     import torch.distributed as dist
     try:
@@ -121,8 +128,7 @@ def _gather_images_nccl(local: Optional[torch.Tensor], idx: Sequence[int], B: in
         block[: local.shape[0]] = local
     allb = torch.empty((world * per,) + tuple(shape), dtype=torch.float32, device=device)
     dist.all_gather_into_tensor(allb, block, group=group)
-    # rank r's j-th patch is global patch r + j * world  ->  position r * per + j of the gathered blocks
-    order = torch.tensor([(i % world) * per + i // world for i in range(B)], dtype=torch.long, device=device)
+    order = torch.tensor(gather_order(B, world), dtype=torch.long, device=device)
     return allb.index_select(0, order)
 
 

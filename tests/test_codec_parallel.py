@@ -156,3 +156,37 @@ def test_container_round_trip_and_damage_detection():
     for k, v in (("min_z", [-2 ** 31, 5, -9]), ("max_y", [-40, 264, 264])):
         with pytest.raises(K.ContainerError):
             K.unpack(K.pack({**comp, k: v}))
+
+
+def test_gather_order_inverts_the_round_robin_sharding():
+    """decompress_sharded over NCCL gathers equal-sized, zero-padded blocks (rank r: patches r, r+W, ...) and re-orders them with
+    gather_order: for every batch size and world size, including ragged and idle ranks, that re-ordering is the identity on patch ids."""
+    from domain_specific_image_compression_b200 import codec_parallel as CP
+    for world in (1, 2, 3, 4, 8):
+        for B in (1, 2, 5, 8, 13, 16, 17):
+            per = (B + world - 1) // world
+            blocks = []
+            for r in range(world):
+                idx = CP.patch_indices(B, r, world)
+                blocks += idx + [-1] * (per - len(idx))            # -1 = padding rows of the all_gather block
+            got = [blocks[k] for k in CP.gather_order(B, world)]
+            assert got == list(range(B)), (world, B)
+
+
+def test_training_only_fast_paths_are_off_by_default_and_gated():
+    """The library default must reproduce the reference bit for bit: the three training-only switches are off, and the layer
+    predicates refuse eval mode, CPU tensors and shapes the kernels do not cover."""
+    import torch
+    import torch.nn as nn
+    from domain_specific_image_compression_b200 import layers as L, model as M
+    assert L.FUSE_FIRST_LAYER is False and L.FAST_LAST_LAYER is False and M.OVERLAP_HYPER_BRANCH is False
+    conv, gdn = nn.Conv2d(3, 128, 3, 1, 1), L.GDN(128)
+    x = torch.rand(1, 3, 16, 16)
+    try:
+        L.FUSE_FIRST_LAYER = L.FAST_LAST_LAYER = True
+        assert not L._first_layer_fusable(conv, gdn, x, True)                       # CPU tensor
+        assert not L._first_layer_fusable(conv, gdn, x, False)                      # eval mode
+        assert not L._last_layer_fast(nn.ConvTranspose2d(128, 3, 5, 2, 2, output_padding=1), x, True)    # CPU tensor
+        assert not L._last_layer_fast(nn.ConvTranspose2d(128, 3, 5, 2, 2, output_padding=1), x, False)
+    finally:
+        L.FUSE_FIRST_LAYER = L.FAST_LAST_LAYER = False
