@@ -260,7 +260,15 @@ __global__ void __launch_bounds__(256) dgamma_fold_kernel(const float *__restric
     const int e = blockIdx.x * 256 + threadIdx.x;
     if (e >= CC) return;
     float s = 0.f;
-    for (int c = 0; c < n_part; ++c) s += partial[(size_t)c * CC + e];
+    int c = 0;
+    for (; c + 8 <= n_part; c += 8) {                    // eight independent loads in flight, summed in index order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcs(partial + (size_t)(c + u) * CC + e);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; c < n_part; ++c) s += __ldcs(partial + (size_t)c * CC + e);
     out[e] = s;
 }
 
