@@ -58,7 +58,8 @@ def parse():
     ap.add_argument("--no-gpu-eager-baseline", action="store_true")
     ap.add_argument("--gdn", default="diag", choices=["diag", "dense"], help="diag: the reference's path (layers.py:21); dense: all 13 "
                     "GDN/IGDN sites use the C x C gamma on tcgen05 tensor cores (north_star's contraction), forward and backward")
-    ap.add_argument("--bucket-mb", type=float, default=6.0, help="gradient bucket size for the overlapped all-reduce")
+    ap.add_argument("--bucket-mb", type=float, default=None, help="gradient bucket size for the overlapped all-reduce (default: 6 MB at N > 1, "
+                    "one bucket at N = 1 where there is nothing to overlap)")
     ap.add_argument("--nchw", action="store_true", help="keep activations NCHW (default: torch.channels_last, which saves cuDNN's "
                     "internal NCHW<->NHWC transposes; GDN kernels run natively in either layout)")
     ap.add_argument("--no-cudnn-benchmark", action="store_true", help="cuDNN autotune is on by default (warm-up steps absorb it)")
@@ -272,7 +273,7 @@ def run_ours(args):
     from domain_specific_image_compression_b200 import model as _model
     _model.OVERLAP_HYPER_BRANCH = not args.no_overlap_hyper
     model = model.to(memory_format=fmt)
-    trainer = FlatTrainer(model, lr=1e-4, betas=(0.9, 0.999), grad_clip=1.0, bucket_bytes=int(args.bucket_mb * (1 << 20)))
+    trainer = FlatTrainer(model, lr=1e-4, betas=(0.9, 0.999), grad_clip=1.0, bucket_bytes=None if args.bucket_mb is None else int(args.bucket_mb * (1 << 20)))
     x_dev = synthetic_batch(B, H, W, 42 + rank, dev).contiguous(memory_format=fmt)
     x_host = x_dev.cpu().pin_memory()
     x_stage = torch.empty_like(x_dev)

@@ -56,7 +56,14 @@ PROTOTYPES = {
     "sic_ssim_fwd": (_i, [_p, _p, _i, _i, _i, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p]),
     "sic_ssim_fwd_pool": (_i, [_p, _p, _i, _i, _i, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p, _p, _p]),
     "sic_ssim_bwd_pool": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "sic_ssim_fwd_ex": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, ctypes.c_float, ctypes.c_float, _p, _p, _p, _p, _p, _p]),
+    "sic_ssim_bwd_ex": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "sic_msssim_combine": (_i, [_p, _p, _p, _p, _i, _i, _p, _i, _p, _p, _p]),
     "sic_ssim_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
+    "sic_rd_loss_fwd": (_i, [_p, _i, _p, _i, _p, _i, _l, ctypes.c_float, _p, _p, _p, _p, _p]),
+    "sic_rd_loss_bwd": (_i, [_p, _p, _l, ctypes.c_float, _i, _i, _i, _p, _p, _p, _p]),
+    "sic_clip_adam_workspace_bytes": (_z, [_l]),
+    "sic_clip_adam_step": (_i, [_p, _p, _p, _p, _l, _p] + [ctypes.c_float] * 7 + [_p, _p, _z, _p]),
     "sic_quantize_indices": (_i, [_p, _i, _l, _i, _i, _p, _p, _p, _p]),
     "sic_build_cdf_tables": (_i, [_i, _p, _p, _i, _i, _i, _p, _p, _i, _p, _p]),
     "sic_rans_encode": (_i, [_p, _p, _p, _i, _l, _l, _l, _i, _p, _l, _p, _p]),

@@ -35,6 +35,7 @@ SOURCES = [
     ("deconv_rgb.cu", []),
     ("msssim.cu", []),
     ("hyper_tail.cu", []),
+    ("train_step.cu", []),
     ("tables.cu", ["-fmad=false"]),
     ("rans_host.cpp", []),
     ("rans_device.cu", []),

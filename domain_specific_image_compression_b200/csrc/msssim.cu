@@ -28,23 +28,40 @@ __constant__ float c_g[kK] = {1.028380357e-03f, 7.598758209e-03f, 3.600077331e-0
 
 // ---- forward ---------------------------------------------------------------------------------------------------------
 // maps (nullable): [5][planes][Hv][Wv] = M2mu, M2xx, M2xy, l, T   (see ssim_bwd_kernel)
+// Layout of an image operand: bands == 0: planar [planes, H, W]; bands == C: channels-last [B, H, W, C] with plane = b * C + c (what the
+// fused last synthesis layer writes and the fused first analysis layer reads) - element stride C, no conversion pass either way.
+struct PlaneView {
+    long base;
+    int stride;
+};
+__device__ __forceinline__ PlaneView plane_view(int plane, int bands, int H, int W) {
+    if (bands == 0) return {(long)plane * H * W, 1};
+    const int b = plane / bands;
+    return {(long)b * H * W * bands + (plane - b * bands), bands};
+}
+
+// clamp01: X is clamped to [0, 1] as it is staged (the x_hat.clamp(0, 1) of model.py:98 without its own pass)
 __global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(const float *__restrict__ X, const float *__restrict__ Y, int H, int W,
-                                                            float c1, float c2, float *__restrict__ part_ss,
-                                                            float *__restrict__ part_cs, float *__restrict__ maps, long map_stride,
-                                                            float *__restrict__ x_pool, float *__restrict__ y_pool) {
+                                                            int x_bands, int y_bands, int clamp01, float c1, float c2,
+                                                            float *__restrict__ part_ss, float *__restrict__ part_cs,
+                                                            float *__restrict__ maps, long map_stride, float *__restrict__ x_pool,
+                                                            float *__restrict__ y_pool) {
     __shared__ float sx[kHalo][kHalo + 1], sy[kHalo][kHalo + 1];
     __shared__ float hb[5][kHalo][kT + 1];
     __shared__ float red[2][kThreads / 32];
     const int plane = blockIdx.z;
     const int Hv = H - (kK - 1), Wv = W - (kK - 1);
     const int oy0 = blockIdx.y * kT, ox0 = blockIdx.x * kT;
-    const float *xp = X + (long)plane * H * W, *yp = Y + (long)plane * H * W;
+    const PlaneView vx = plane_view(plane, x_bands, H, W), vy = plane_view(plane, y_bands, H, W);
+    const float *xp = X + vx.base, *yp = Y + vy.base;
     for (int i = threadIdx.x; i < kHalo * kHalo; i += kThreads) {
         int r = i / kHalo, c = i - r * kHalo;
         int gy = oy0 + r, gx = ox0 + c;
         bool in = gy < H && gx < W;
-        sx[r][c] = in ? __ldg(xp + (long)gy * W + gx) : 0.f;
-        sy[r][c] = in ? __ldg(yp + (long)gy * W + gx) : 0.f;
+        float xv = in ? __ldg(xp + ((long)gy * W + gx) * vx.stride) : 0.f;
+        if (clamp01) xv = fminf(fmaxf(xv, 0.f), 1.f);
+        sx[r][c] = xv;
+        sy[r][c] = in ? __ldg(yp + ((long)gy * W + gx) * vy.stride) : 0.f;
     }
     __syncthreads();
     if (x_pool != nullptr) {
@@ -125,17 +142,22 @@ __global__ void __launch_bounds__(kThreads) ssim_fwd_kernel(const float *__restr
 // F = g_ss[plane] * mean(ss) + g_cs[plane] * mean(cs).  With k = g_ss*l + g_cs (per pixel):
 //   M_mu = g_ss*T + k*M2mu ,  M_xx = k*M2xx ,  M_xy = k*M2xy          (all scaled by 1/n_valid)
 //   dF/dX(q) = sum_p G(p..q) M_mu(p) + 2 X(q) sum_p G M_xx(p) + Y(q) sum_p G M_xy(p)      (transposed window: q = p + tap)
+// g_scale (nullable): device scalar multiplying g_ss and g_cs (the gradient arriving at the MS-SSIM value, when g_ss / g_cs hold the
+// derivatives of that value w.r.t. this scale's means: sic_msssim_combine).  dX has the layout of X; with clamp01 it is zero where
+// X lies outside [0, 1] (the backward of the clamp folded into the forward's staging).
 __global__ void __launch_bounds__(kThreads) ssim_bwd_kernel(const float *__restrict__ X, const float *__restrict__ Y,
                                                             const float *__restrict__ maps, long map_stride,
-                                                            const float *__restrict__ g_ss, const float *__restrict__ g_cs, int H, int W,
-                                                            const float *__restrict__ g_pool, float *__restrict__ dX) {
+                                                            const float *__restrict__ g_ss, const float *__restrict__ g_cs,
+                                                            const float *__restrict__ g_scale, int H, int W, int x_bands, int y_bands,
+                                                            int clamp01, const float *__restrict__ g_pool, float *__restrict__ dX) {
     __shared__ float sm[3][kHalo][kHalo + 1];
     __shared__ float hb[3][kHalo][kT + 1];
     const int plane = blockIdx.z;
     const int Hv = H - (kK - 1), Wv = W - (kK - 1);
     const int qy0 = blockIdx.y * kT, qx0 = blockIdx.x * kT;
-    const float inv_n = 1.0f / ((float)Hv * (float)Wv);
+    const float inv_n = (g_scale ? __ldg(g_scale) : 1.f) / ((float)Hv * (float)Wv);
     const float gs = (g_ss ? __ldg(g_ss + plane) : 0.f) * inv_n, gc = (g_cs ? __ldg(g_cs + plane) : 0.f) * inv_n;
+    const PlaneView vx = plane_view(plane, x_bands, H, W), vy = plane_view(plane, y_bands, H, W);
     const float *mp = maps + (long)plane * Hv * Wv;
     for (int i = threadIdx.x; i < kHalo * kHalo; i += kThreads) {
         int r = i / kHalo, c = i - r * kHalo;
@@ -179,16 +201,91 @@ __global__ void __launch_bounds__(kThreads) ssim_bwd_kernel(const float *__restr
                 b1 = fmaf(g, hb[1][rr][c], b1);
                 b2 = fmaf(g, hb[2][rr][c], b2);
             }
-            long o = (long)plane * H * W + (long)qy * W + qx;
-            float d = b0 + 2.f * __ldg(X + o) * b1 + __ldg(Y + o) * b2;
+            const long q = (long)qy * W + qx, o = vx.base + q * vx.stride;
+            const float xraw = __ldg(X + o);
+            const float xv = clamp01 ? fminf(fmaxf(xraw, 0.f), 1.f) : xraw;
+            float d = b0 + 2.f * xv * b1 + __ldg(Y + vy.base + q * vy.stride) * b2;
             // the gradient that arrives through the pooled copy of X (the coarser scales): avg_pool2d backward, 1/4 to each of the four
             if (g_pool != nullptr) d = fmaf(0.25f, __ldg(g_pool + (long)plane * (H >> 1) * (W >> 1) + (long)(qy >> 1) * (W >> 1) + (qx >> 1)), d);
+            if (clamp01 && !(xraw >= 0.f && xraw <= 1.f)) d = 0.f;                  // clamp backward: the gradient passes inside [0, 1] only
             dX[o] = d;
         }
     }
 }
 
+// ---- combination of the scales -----------------------------------------------------------------------------------------
+// piq.multi_scale_ssim's tail (restated in losses.py): per (image, band) plane  prod_{l < L-1} relu(mean cs_l)^w_l * relu(mean ss_{L-1})^w_{L-1},
+// weights normalised by their sum, then the mean over bands and images - and, for the backward, the derivative of that value
+// with respect to every per-plane mean (what ssim_bwd_kernel takes as g_ss / g_cs).  One CTA: the data is L x 2 x planes x tiles floats.
+// Replaces ~13 tiny torch launches forward and ~20 backward per training step (profiles/r02ap_ncu_launches_bench_step.txt).
+constexpr int kMaxLevels = 8;
+struct CombineArgs {
+    int levels, planes, normalize;   // normalize: weights divided by their sum (piq does that to user-supplied weights, not to its defaults)
+    int tiles[kMaxLevels];
+    long off[kMaxLevels];        // level l: part_ss at part + off[l], part_cs at part + off[l] + planes * tiles[l]
+    float inv_n[kMaxLevels];     // 1 / ((H_l - 10)(W_l - 10))
+};
+
+__global__ void __launch_bounds__(kThreads) msssim_combine_kernel(const float *__restrict__ part, const float *__restrict__ weights,
+                                                                  CombineArgs a, float *__restrict__ out, float *__restrict__ coef) {
+    __shared__ float red[kThreads / 32];
+    const int L = a.levels;
+    float w[kMaxLevels], wsum = 0.f;
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) {
+        w[l] = l < L ? __ldg(weights + l) : 0.f;
+        wsum += w[l];
+    }
+    if (!a.normalize) wsum = 1.f;
+    const float inv_planes = 1.0f / (float)a.planes;
+    float acc = 0.f;
+    for (int plane = threadIdx.x; plane < a.planes; plane += kThreads) {
+        float t[kMaxLevels], pw[kMaxLevels];
+        float prod = 1.f;
+#pragma unroll
+        for (int l = 0; l < kMaxLevels; ++l) {
+            t[l] = 0.f;
+            pw[l] = 1.f;
+            if (l < L) {
+                // the last scale contributes its SSIM mean, the others their contrast-structure mean; fixed-order fold of the tiles
+                const float *src = part + a.off[l] + (l == L - 1 ? 0 : (long)a.planes * a.tiles[l]) + (long)plane * a.tiles[l];
+                float sum = 0.f;
+                for (int k = 0; k < a.tiles[l]; ++k) sum += __ldg(src + k);
+                t[l] = fmaxf(sum * a.inv_n[l], 0.f);
+                pw[l] = powf(t[l], w[l] / wsum);
+                prod *= pw[l];
+            }
+        }
+        acc += prod;
+        if (coef != nullptr) {
+#pragma unroll
+            for (int l = 0; l < kMaxLevels; ++l) {
+                if (l < L) {
+                    float others = 1.f;
+#pragma unroll
+                    for (int k = 0; k < kMaxLevels; ++k)
+                        if (k < L && k != l) others *= pw[k];
+                    const float wl = w[l] / wsum;
+                    const float d = t[l] > 0.f ? inv_planes * others * wl * powf(t[l], wl - 1.f) : 0.f;      // relu: nothing passes at <= 0
+                    coef[((long)l * 2 + 0) * a.planes + plane] = l == L - 1 ? d : 0.f;                        // d value / d mean ss_l
+                    coef[((long)l * 2 + 1) * a.planes + plane] = l == L - 1 ? 0.f : d;                        // d value / d mean cs_l
+                }
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < kThreads / 32; ++wq) s += red[wq];
+        *out = s * inv_planes;
+    }
+}
+
 SIC_REGISTER_KERNEL("ssim_fwd_kernel", ssim_fwd_kernel);
+SIC_REGISTER_KERNEL("msssim_combine_kernel", msssim_combine_kernel);
 SIC_REGISTER_KERNEL("ssim_bwd_kernel", ssim_bwd_kernel);
 }  // namespace
 }  // namespace sic
@@ -200,19 +297,27 @@ extern "C" long sic_ssim_tiles(int H, int W) {
     return (long)((H - 10 + kT - 1) / kT) * ((W - 10 + kT - 1) / kT);
 }
 
-extern "C" int sic_ssim_fwd_pool(const float *X, const float *Y, int planes, int H, int W, float c1, float c2, float *part_ss,
-                                 float *part_cs, float *maps, float *x_pool, float *y_pool, void *stream) {
+extern "C" int sic_ssim_fwd_ex(const float *X, const float *Y, int planes, int H, int W, int x_bands, int y_bands, int clamp01, float c1,
+                               float c2, float *part_ss, float *part_cs, float *maps, float *x_pool, float *y_pool, void *stream) {
     SIC_CHECK_ARG(planes > 0 && H >= 11 && W >= 11, "sic_ssim_fwd: needs planes > 0 and images of at least 11x11 (got %d, %dx%d)", planes, H, W);
     SIC_CHECK_ARG(X && Y && part_ss && part_cs, "sic_ssim_fwd: null pointer");
     SIC_CHECK_ARG(planes <= 65535, "sic_ssim_fwd: more than 65535 (batch x channel) planes");
+    SIC_CHECK_ARG(x_bands >= 0 && y_bands >= 0 && (x_bands == 0 || planes % x_bands == 0) && (y_bands == 0 || planes % y_bands == 0),
+                  "sic_ssim_fwd: bands (%d, %d) must be 0 (planar) or divide planes = %d (channels-last)", x_bands, y_bands, planes);
     SIC_CHECK_ARG((x_pool == nullptr) == (y_pool == nullptr), "sic_ssim_fwd_pool: x_pool and y_pool go together");
     SIC_CHECK_ARG(x_pool == nullptr || ((H | W) & 1) == 0, "sic_ssim_fwd_pool: pooled outputs need even H and W (got %dx%d)", H, W);
     cudaStream_t st = (cudaStream_t)stream;
     const int Hv = H - 10, Wv = W - 10;
     dim3 grid((Wv + kT - 1) / kT, (Hv + kT - 1) / kT, planes);
-    ssim_fwd_kernel<<<grid, kThreads, 0, st>>>(X, Y, H, W, c1, c2, part_ss, part_cs, maps, (long)planes * Hv * Wv, x_pool, y_pool);
+    ssim_fwd_kernel<<<grid, kThreads, 0, st>>>(X, Y, H, W, x_bands, y_bands, clamp01, c1, c2, part_ss, part_cs, maps,
+                                               (long)planes * Hv * Wv, x_pool, y_pool);
     SIC_CHECK_LAUNCH("sic_ssim_fwd");
     return 0;
+}
+
+extern "C" int sic_ssim_fwd_pool(const float *X, const float *Y, int planes, int H, int W, float c1, float c2, float *part_ss,
+                                 float *part_cs, float *maps, float *x_pool, float *y_pool, void *stream) {
+    return sic_ssim_fwd_ex(X, Y, planes, H, W, 0, 0, 0, c1, c2, part_ss, part_cs, maps, x_pool, y_pool, stream);
 }
 
 extern "C" int sic_ssim_fwd(const float *X, const float *Y, int planes, int H, int W, float c1, float c2, float *part_ss,
@@ -220,21 +325,53 @@ extern "C" int sic_ssim_fwd(const float *X, const float *Y, int planes, int H, i
     return sic_ssim_fwd_pool(X, Y, planes, H, W, c1, c2, part_ss, part_cs, maps, nullptr, nullptr, stream);
 }
 
-extern "C" int sic_ssim_bwd_pool(const float *X, const float *Y, const float *maps, const float *g_ss, const float *g_cs,
-                                 const float *g_pool, int planes, int H, int W, float *dX, void *stream) {
+extern "C" int sic_ssim_bwd_ex(const float *X, const float *Y, const float *maps, const float *g_ss, const float *g_cs,
+                               const float *g_scale, const float *g_pool, int planes, int H, int W, int x_bands, int y_bands, int clamp01,
+                               float *dX, void *stream) {
     SIC_CHECK_ARG(planes > 0 && H >= 11 && W >= 11, "sic_ssim_bwd: bad extents");
     SIC_CHECK_ARG(X && Y && maps && dX, "sic_ssim_bwd: null pointer");
     SIC_CHECK_ARG(planes <= 65535, "sic_ssim_bwd: more than 65535 (batch x channel) planes");
+    SIC_CHECK_ARG(x_bands >= 0 && y_bands >= 0 && (x_bands == 0 || planes % x_bands == 0) && (y_bands == 0 || planes % y_bands == 0),
+                  "sic_ssim_bwd: bands (%d, %d) must be 0 (planar) or divide planes = %d (channels-last)", x_bands, y_bands, planes);
     SIC_CHECK_ARG(g_pool == nullptr || ((H | W) & 1) == 0, "sic_ssim_bwd_pool: a pooled gradient needs even H and W (got %dx%d)", H, W);
     cudaStream_t st = (cudaStream_t)stream;
     const int Hv = H - 10, Wv = W - 10;
     dim3 grid((W + kT - 1) / kT, (H + kT - 1) / kT, planes);
-    ssim_bwd_kernel<<<grid, kThreads, 0, st>>>(X, Y, maps, (long)planes * Hv * Wv, g_ss, g_cs, H, W, g_pool, dX);
+    ssim_bwd_kernel<<<grid, kThreads, 0, st>>>(X, Y, maps, (long)planes * Hv * Wv, g_ss, g_cs, g_scale, H, W, x_bands, y_bands, clamp01,
+                                               g_pool, dX);
     SIC_CHECK_LAUNCH("sic_ssim_bwd");
     return 0;
+}
+
+extern "C" int sic_ssim_bwd_pool(const float *X, const float *Y, const float *maps, const float *g_ss, const float *g_cs,
+                                 const float *g_pool, int planes, int H, int W, float *dX, void *stream) {
+    return sic_ssim_bwd_ex(X, Y, maps, g_ss, g_cs, nullptr, g_pool, planes, H, W, 0, 0, 0, dX, stream);
 }
 
 extern "C" int sic_ssim_bwd(const float *X, const float *Y, const float *maps, const float *g_ss, const float *g_cs, int planes,
                             int H, int W, float *dX, void *stream) {
     return sic_ssim_bwd_pool(X, Y, maps, g_ss, g_cs, nullptr, planes, H, W, dX, stream);
+}
+
+extern "C" int sic_msssim_combine(const float *part, const long *offsets, const int *tiles, const long *n_valid, int levels, int planes,
+                                  const float *weights, int normalize, float *out, float *coef, void *stream) {
+    SIC_CHECK_ARG(levels >= 1 && levels <= kMaxLevels, "sic_msssim_combine: %d scales (1..%d supported)", levels, kMaxLevels);
+    SIC_CHECK_ARG(planes > 0, "sic_msssim_combine: no planes");
+    SIC_CHECK_ARG(part && offsets && tiles && n_valid && weights && out, "sic_msssim_combine: null pointer");
+    CombineArgs a;
+    a.levels = levels;
+    a.planes = planes;
+    a.normalize = normalize != 0;
+    for (int l = 0; l < kMaxLevels; ++l) {
+        a.tiles[l] = l < levels ? tiles[l] : 0;
+        a.off[l] = l < levels ? offsets[l] : 0;
+        a.inv_n[l] = 1.f;
+        if (l < levels) {
+            SIC_CHECK_ARG(tiles[l] > 0 && n_valid[l] > 0 && offsets[l] >= 0, "sic_msssim_combine: bad geometry of scale %d", l);
+            a.inv_n[l] = 1.0f / (float)n_valid[l];
+        }
+    }
+    msssim_combine_kernel<<<1, kThreads, 0, (cudaStream_t)stream>>>(part, weights, a, out, coef);
+    SIC_CHECK_LAUNCH("sic_msssim_combine");
+    return 0;
 }

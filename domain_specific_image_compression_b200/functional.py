@@ -593,6 +593,89 @@ def ssim_stats(x: torch.Tensor, y: torch.Tensor, c1: float = 0.01 ** 2, c2: floa
     return (ss, cs, xp, yp) if pool else (ss, cs)
 
 
+class _MSSSIM(torch.autograd.Function):
+    """All scales of the MS-SSIM value in L + 1 launches forward (one statistics kernel per scale, each also writing the next
+    scale's pooled inputs, then the combination kernel) and L launches backward (coarsest scale first; each hands its dX to the next
+    finer one as the pooled gradient).  No torch op in between: the clamp of the reconstruction, the layout of both images
+    (planar or channels-last), the fold of the partial sums, relu / pow / product / mean and the incoming gradient's scale all
+    live in the kernels."""
+
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, x, y, weights, normalize: bool, c1: float, c2: float, clamp01: bool):
+        lib = _lib.load()
+        x, x_cl = _dense_layout(x, "x")
+        y, y_cl = _dense_layout(y, "y")
+        weights = _require_cuda_f32(weights, "scale_weights")
+        if x.shape != y.shape or x.dim() != 4:
+            raise _lib.SicError("multi_scale_ssim expects two [B,C,H,W] tensors of the same shape")
+        B, C, H, W = x.shape
+        L, planes = weights.numel(), B * C
+        sizes = [(H >> l, W >> l) for l in range(L)]
+        if any((h | w) & 1 for h, w in sizes[:-1]) or sizes[-1][0] < 11 or sizes[-1][1] < 11:
+            raise _lib.SicError("multi_scale_ssim (fused): every pooled scale needs even H and W and the last one at least 11x11")
+        tiles = [int(lib.sic_ssim_tiles(h, w)) for h, w in sizes]
+        offs, total = [], 0
+        for t in tiles:
+            offs.append(total)
+            total += 2 * planes * t
+        need = ctx.needs_input_grad[0]
+        part = torch.empty(total, dtype=torch.float32, device=x.device)
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        coef = torch.empty((L, 2, planes), dtype=torch.float32, device=x.device) if need else None
+        saved, xs, ys = [], x, y
+        with torch.cuda.device(x.device):
+            for l, (h, w) in enumerate(sizes):
+                first, last = l == 0, l == L - 1
+                maps = torch.empty((5, planes, h - 10, w - 10), dtype=torch.float32, device=x.device) if need else None
+                xp = None if last else torch.empty((B, C, h // 2, w // 2), dtype=torch.float32, device=x.device)
+                yp = None if last else torch.empty_like(xp)
+                ps = part[offs[l]:offs[l] + planes * tiles[l]]
+                pc = part[offs[l] + planes * tiles[l]:offs[l] + 2 * planes * tiles[l]]
+                _launch(lib.sic_ssim_fwd_ex(_ptr(xs), _ptr(ys), planes, h, w, C if (first and x_cl) else 0, C if (first and y_cl) else 0,
+                                            int(bool(clamp01) and first), c1, c2, _ptr(ps), _ptr(pc), _ptr(maps), _ptr(xp), _ptr(yp),
+                                            _stream()), "sic_ssim_fwd_ex")
+                saved += [xs, ys, maps]
+                xs, ys = xp, yp
+            _launch(lib.sic_msssim_combine(_ptr(part), (ctypes.c_long * L)(*offs), (ctypes.c_int * L)(*tiles),
+                                           (ctypes.c_long * L)(*[(h - 10) * (w - 10) for h, w in sizes]), L, planes, _ptr(weights),
+                                           int(bool(normalize)), _ptr(out), _ptr(coef), _stream()), "sic_msssim_combine")
+        if need:
+            ctx.save_for_backward(coef, *saved)
+            ctx.geom = (sizes, planes, C, x_cl, y_cl, bool(clamp01))
+        return out
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        coef, *saved = ctx.saved_tensors
+        sizes, planes, C, x_cl, y_cl, clamp01 = ctx.geom
+        L = len(sizes)
+        g_out = _require_cuda_f32(g_out, "grad of the MS-SSIM value")
+        g_pool = None
+        with torch.cuda.device(g_out.device):
+            for l in range(L - 1, -1, -1):
+                h, w = sizes[l]
+                xs, ys, maps = saved[3 * l], saved[3 * l + 1], saved[3 * l + 2]
+                first, last = l == 0, l == L - 1
+                dx = torch.empty_like(xs)                      # level 0: the layout of x (dense NCHW or channels-last) is kept
+                _launch(lib.sic_ssim_bwd_ex(_ptr(xs), _ptr(ys), _ptr(maps), _ptr(coef[l, 0]) if last else None,
+                                            None if last else _ptr(coef[l, 1]), _ptr(g_out), _ptr(g_pool), planes, h, w,
+                                            C if (first and x_cl) else 0, C if (first and y_cl) else 0, int(clamp01 and first), _ptr(dx),
+                                            _stream()), "sic_ssim_bwd_ex")
+                g_pool = dx
+        return g_pool, None, None, None, None, None, None
+
+
+def msssim_fused(x: torch.Tensor, y: torch.Tensor, scale_weights: torch.Tensor, normalize: bool = True, c1: float = 0.01 ** 2,
+                 c2: float = 0.03 ** 2, clamp01: bool = False) -> torch.Tensor:
+    """MS-SSIM value (0-dim) of x against the target y over len(scale_weights) dyadic scales, differentiable w.r.t. x only; every scale
+    that is pooled must have even H and W (losses.multi_scale_ssim falls back to the per-scale kernels + torch pooling otherwise).
+    scale_weights: CUDA float32 [L]; normalize: divide them by their sum (inside the kernel).  clamp01: x is clamped to [0, 1] first."""
+    return _MSSSIM.apply(x, y, scale_weights, bool(normalize), float(c1), float(c2), bool(clamp01))
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # K4 / K3 / E1
 def quantize_indices(q: torch.Tensor, do_round: bool = False, tail: int = 10, want_symbols: bool = True):
@@ -699,3 +782,75 @@ def rans_decode_device(data: torch.Tensor, nbytes: torch.Tensor, tables: torch.T
         _launch(lib.sic_rans_decode(_ptr(data), _ptr(nbytes), _ptr(tables), _ptr(Ls), S, int(n), int(sym_per_row), int(rows_per_stream),
                                     tables.shape[-1], cap, _ptr(sym), _ptr(status), _stream()), "sic_rans_decode")
     return sym, status
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# (e) training-step tail on the flat buffers
+def clip_adam_workspace(n: int, device: torch.device) -> torch.Tensor:
+    lib = _lib.load()
+    return torch.empty(max(int(lib.sic_clip_adam_workspace_bytes(int(n))), 8) // 8, dtype=torch.float64, device=device)
+
+
+def clip_adam_step(param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: torch.Tensor,
+                   norm_out: Optional[torch.Tensor], workspace: torch.Tensor, *, inv_world: float, clip: float, lr: float,
+                   betas: Tuple[float, float], eps: float, weight_decay: float) -> None:
+    """Global-norm clip (train.py:200-202) + Adam (train.py:182-183) on flat float32 buffers, in place, two launches; `step` is the
+    device-side update counter (float32 scalar, incremented by the call), `norm_out` receives the pre-clip norm of the mean gradient."""
+    global launch_count
+    lib = _lib.load()
+    for name, t in (("param", param), ("grad", grad), ("exp_avg", exp_avg), ("exp_avg_sq", exp_avg_sq)):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 1 and t.is_contiguous()):
+            raise _lib.SicError(f"clip_adam_step: {name} must be a flat contiguous CUDA float32 tensor")
+        if t.numel() != param.numel():
+            raise _lib.SicError(f"clip_adam_step: {name} has {t.numel()} elements, param has {param.numel()}")
+    if step.dtype != torch.float32 or step.numel() != 1 or not step.is_cuda:
+        raise _lib.SicError("clip_adam_step: step must be a CUDA float32 scalar")
+    with torch.cuda.device(param.device):
+        _launch(lib.sic_clip_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), _ptr(step),
+                                       float(inv_world), float(clip or 0.0), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                       float(weight_decay), _ptr(norm_out), _ptr(workspace), workspace.numel() * 8, _stream()),
+                "sic_clip_adam_step")
+    launch_count += 1
+
+
+class _RDLossTail(torch.autograd.Function):
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, bits_y, bits_z, dist, pixels: int, lambda_rd: float, similarity: bool):
+        lib = _lib.load()
+        bits_y = _require_cuda_f32(bits_y, "bits_y").reshape(-1)
+        bits_z = _require_cuda_f32(bits_z, "bits_z").reshape(-1)
+        dist = _require_cuda_f32(dist, "distortion value")
+        if dist.numel() != 1:
+            raise _lib.SicError("rd_loss_tail: the distortion must be a scalar")
+        dev = bits_y.device
+        loss, R, D, keep = (torch.empty((), dtype=torch.float32, device=dev) for _ in range(4))
+        with torch.cuda.device(dev):
+            _launch(lib.sic_rd_loss_fwd(_ptr(bits_y), bits_y.numel(), _ptr(bits_z), bits_z.numel(), _ptr(dist), int(similarity), int(pixels),
+                                        float(lambda_rd), _ptr(loss), _ptr(R), _ptr(D), _ptr(keep), _stream()), "sic_rd_loss_fwd")
+        ctx.save_for_backward(keep)
+        ctx.geom = (bits_y.numel(), bits_z.numel(), int(pixels), float(lambda_rd), bool(similarity), dist.shape)
+        ctx.mark_non_differentiable(R, D)
+        return loss, R, D
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g_loss, _g_R, _g_D):
+        lib = _lib.load()
+        (keep,) = ctx.saved_tensors
+        ny, nz, pixels, lambda_rd, similarity, dshape = ctx.geom
+        g_loss = _require_cuda_f32(g_loss, "g_loss")
+        gy = torch.empty(ny, dtype=torch.float32, device=keep.device)
+        gz = torch.empty(nz, dtype=torch.float32, device=keep.device)
+        gd = torch.empty(dshape, dtype=torch.float32, device=keep.device)
+        with torch.cuda.device(keep.device):
+            _launch(lib.sic_rd_loss_bwd(_ptr(g_loss), _ptr(keep), pixels, lambda_rd, int(similarity), ny, nz, _ptr(gy), _ptr(gz), _ptr(gd),
+                                        _stream()), "sic_rd_loss_bwd")
+        return gy, gz, gd, None, None, None
+
+
+def rd_loss_tail(bits_y: torch.Tensor, bits_z: torch.Tensor, dist: torch.Tensor, pixels: int, lambda_rd: float, similarity: bool):
+    """(loss, R, D) of model.py:75-107 from the per-patch bit counts of y and z and the distortion value (the MS-SSIM when
+    `similarity`, else the MSE): R = max((sum bits_y + sum bits_z) / pixels, 0), D = 1 - dist | dist, loss = lambda D + R.
+    One launch forward, one backward; R and D carry no gradient (the reference returns them detached)."""
+    return _RDLossTail.apply(bits_y, bits_z, dist, int(pixels), float(lambda_rd), bool(similarity))

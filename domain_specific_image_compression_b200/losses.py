@@ -18,13 +18,14 @@ from . import _lib
 from . import functional as F_sic
 
 
-def multi_scale_ssim(x, y, data_range=1.0, scale_weights=None, kernel_size=11, kernel_sigma=1.5, k1=0.01, k2=0.03):
+def multi_scale_ssim(x, y, data_range=1.0, scale_weights=None, kernel_size=11, kernel_sigma=1.5, k1=0.01, k2=0.03, clamp01=False):
+    """clamp01=True folds the x.clamp(0, 1) the reference applies to the reconstruction first (model.py:98) into the kernels."""
+    normalize = scale_weights is not None      # piq normalises user-supplied weights, not its defaults
     if scale_weights is None:
-        scale_weights = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], device=x.device, dtype=torch.float32)
+        raw_weights = torch.tensor([0.0448, 0.2856, 0.3001, 0.2363, 0.1333], device=x.device, dtype=torch.float32)
     else:
-        scale_weights = torch.as_tensor(scale_weights, device=x.device, dtype=torch.float32)
-        scale_weights = scale_weights / scale_weights.sum()
-    levels = scale_weights.numel()
+        raw_weights = torch.as_tensor(scale_weights, device=x.device, dtype=torch.float32)
+    levels = raw_weights.numel()
     min_size = (kernel_size - 1) * 2 ** (levels - 1) + 1
     if x.size(-1) < min_size or x.size(-2) < min_size:
         raise ValueError(f"Invalid size of the input images, expected at least {min_size}x{min_size}.")
@@ -35,9 +36,17 @@ def multi_scale_ssim(x, y, data_range=1.0, scale_weights=None, kernel_size=11, k
     # float16 reconstructions arrive here under the reference's autocast training (train.py:196-199): computed in float32
     x, y = x.float(), y.float()
     if float(data_range) != 1.0:              # the reference calls with data_range = 1: no scaling pass (forward and backward) at all
+        if clamp01:                           # the clamp applies to the unscaled reconstruction
+            x, clamp01 = x.clamp(0, 1), False
         x = x / float(data_range)
         y = y / float(data_range)
     c1, c2 = k1 ** 2, k2 ** 2
+    if levels <= 8 and all(((x.size(-2) >> l) | (x.size(-1) >> l)) & 1 == 0 for l in range(levels - 1)):
+        # every pooled scale has even sizes (the training patches): all scales, their combination and the clamp in L + 1 launches
+        return F_sic.msssim_fused(x, y, raw_weights, normalize, c1, c2, clamp01=clamp01)
+    if clamp01:
+        x = x.clamp(0, 1)
+    scale_weights = raw_weights / raw_weights.sum() if normalize else raw_weights
     terms = []
     ssim_last = None
     pooled = None

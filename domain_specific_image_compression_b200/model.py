@@ -285,26 +285,30 @@ def _msssim_weights(device) -> torch.Tensor:
     return w
 
 
-def _total_bits(t: torch.Tensor) -> torch.Tensor:
-    """Sum of a nll map; uses the per-patch bit counts that kernel K1 already reduced (deterministically) when the map
-    came out of this package's forward(), else falls back to summing the tensor like the reference (model.py:77)."""
+def _patch_bits(t: torch.Tensor) -> torch.Tensor:
+    """Bit counts whose sum is the sum of a nll map (model.py:77): the per-patch counts that kernel K1 already reduced
+    (deterministically) when the map came out of this package's forward(), else the map's own sum as a one-element tensor."""
     bits = getattr(t, "_sic_bits", None)
-    return bits.sum() if bits is not None else t.sum()
+    return bits if bits is not None else t.sum().reshape(1)
 
 
 def rate_distortion_loss(out: Dict[str, torch.Tensor], x, lambda_rd=10000.0, dist="mssim"):
     """model.py:75-107."""
     N, C, H, W = x.shape
-    R = (_total_bits(out["nll_y"]) + _total_bits(out["nll_z"])) / (N * H * W)
-    R = torch.clamp(R, min=0.0)
     if dist == "mse":
-        D = F.mse_loss(out["x_hat"], x)
+        d_val, similarity = F.mse_loss(out["x_hat"], x), False
     elif dist == "msssim":
         x_hat = out["x_hat"]
         if x_hat.shape[2:] != x.shape[2:]:
             x_hat = F.interpolate(x_hat, size=x.shape[2:], mode="bilinear", align_corners=False)
-        D = 1.0 - multi_scale_ssim(x_hat.clamp(0, 1), x, data_range=1.0, scale_weights=_msssim_weights(x.device))
+        # the clamp(0, 1) of model.py:98 happens inside the kernels
+        d_val, similarity = multi_scale_ssim(x_hat, x, data_range=1.0, scale_weights=_msssim_weights(x.device), clamp01=True), True
     else:
         raise ValueError("dist must be 'mse' or 'msssim'")
+    by, bz = _patch_bits(out["nll_y"]), _patch_bits(out["nll_z"])
+    if d_val.is_cuda and d_val.dtype == torch.float32 and by.dtype == torch.float32 and bz.dtype == torch.float32:
+        return F_sic.rd_loss_tail(by, bz, d_val, N * H * W, lambda_rd, similarity)       # one launch (and one in the backward)
+    R = torch.clamp((by.sum() + bz.sum()) / (N * H * W), min=0.0)      # host tensors (unit tests of the formula): the reference's op chain
+    D = 1.0 - d_val if similarity else d_val
     loss = lambda_rd * D + R
     return loss, R.detach(), D.detach()

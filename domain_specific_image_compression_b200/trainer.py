@@ -11,7 +11,8 @@ into it) so that
     hyper networks finish first and the 256^2 / 128^2 analysis sites that follow take milliseconds.  Only the last, small
     bucket (the first analysis layers) is exposed.  Round 1 issued one all-reduce after backward() had returned: 7.04 -> 7.20
     ms per step at 8 GPUs with nothing left to hide it under;
-  - global-norm clipping and Adam are three launches on the flat buffer instead of ~80 per-tensor launch groups;
+  - global-norm clipping and Adam are two launches on the flat buffer (csrc/train_step.cu: one pass for the norm, one for the
+    update with the clip coefficient folded in) instead of ~80 per-tensor launch groups;
   - the dead parameters (per GDN site: the CxC `gamma` on the reference's diagonal path, layers.py:13; `gamma_conv.weight`
     when the site runs dense) are simply left out of the bucket — plain
     DistributedDataParallel would need find_unused_parameters for them.
@@ -54,14 +55,21 @@ def _is_dense_permutation(p: torch.Tensor) -> bool:
     return (not p.is_contiguous()) and p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last)
 
 
+def _is_capturing(stream: "torch.cuda.Stream") -> bool:
+    with torch.cuda.stream(stream):
+        return torch.cuda.is_current_stream_capturing()
+
+
 class FlatTrainer:
     def __init__(self, module: torch.nn.Module, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, grad_clip: float = 1.0, process_group=None, fused: Optional[bool] = None,
-                 exclude: Iterable[str] = (), bucket_bytes: int = 6 << 20):
+                 exclude: Iterable[str] = (), bucket_bytes: Optional[int] = None):
         self.module = module
         self.grad_clip = grad_clip
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        if bucket_bytes is None:               # one process: nothing to overlap, one pack launch at the end of backward() instead of five
+            bucket_bytes = (6 << 20) if self.world > 1 else (1 << 62)
         dead = _dead_parameter_names(module) | set(exclude)      # `exclude`: further parameter names the step never touches
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad and n not in dead]
         self.names = [n for n, _ in named]
@@ -83,9 +91,22 @@ class FlatTrainer:
             dist.broadcast(self.flat.detach(), src=0, group=process_group)
         if fused is None:
             fused = self.flat.is_cuda
-        # capturable: the step counter lives on the device, so the whole step can be recorded into a CUDA graph
-        self.opt = torch.optim.Adam([self.flat], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, fused=fused,
-                                    capturable=bool(self.flat.is_cuda))
+        # fused (the default on a GPU): clip + Adam are the two launches of csrc/train_step.cu on the flat buffers; the update
+        # counter and the norm live on the device, so the whole step can be recorded into a CUDA graph.  fused=False keeps
+        # torch.optim.Adam on the flat buffer (the CPU / gloo tests of the host logic, and the comparison in the GPU test).
+        self.fused = bool(fused)
+        self.hyper = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        self.opt = None
+        if self.fused:
+            from . import functional as F_sic
+            self.exp_avg = torch.zeros_like(self.flat)
+            self.exp_avg_sq = torch.zeros_like(self.flat)
+            self.step_count = torch.zeros((), dtype=torch.float32, device=self.flat.device)
+            self.grad_norm = torch.zeros((), dtype=torch.float32, device=self.flat.device)
+            self._opt_ws = F_sic.clip_adam_workspace(total, self.flat.device)
+        else:
+            self.opt = torch.optim.Adam([self.flat], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, fused=False,
+                                        capturable=bool(self.flat.is_cuda))
         self.graph = None
         self.nbytes_allreduce = total * self.flat.element_size()
         # Buckets: contiguous slices of the flat buffer, formed walking the parameters BACKWARDS (the order backward() roughly
@@ -127,9 +148,12 @@ class FlatTrainer:
             # The gradients of one bucket may have been produced on the step's own stream or on the model's side stream
             # (model.OVERLAP_HYPER_BRANCH), and this hook runs on whichever of the two produced the last one: wait for both.
             from .model import _side_streams
+            # While a CUDA graph is being recorded only streams that were forked into the capture may be waited for: a side stream
+            # that exists (another model used it earlier) but did no work in this step is not part of it.
             cur = torch.cuda.current_stream(self.flat_grad.device)
+            capturing = torch.cuda.is_current_stream_capturing()
             for st in (self._main_stream, _side_streams.get(self.flat_grad.device.index)):
-                if st is not None and st != cur:
+                if st is not None and st != cur and (not capturing or _is_capturing(st)):
                     cur.wait_stream(st)
         torch.cat([_flat_in_param_order(self.live[i].grad, self.live[i]) for i in range(a, b)], out=self.flat_grad[lo:hi])
         self.fire_order.append(k)
@@ -150,6 +174,11 @@ class FlatTrainer:
         for w in self._works:                  # stream-level wait (the host does not block on CUDA)
             w.wait()
         self._works = []
+        if self.fused:
+            from . import functional as F_sic
+            F_sic.clip_adam_step(self.flat.detach(), flat_grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.grad_norm,
+                                 self._opt_ws, inv_world=1.0 / self.world, clip=self.grad_clip or 0.0, **self.hyper)
+            return self.grad_norm
         if self.world > 1:
             flat_grad.mul_(1.0 / self.world)
         norm = torch.linalg.vector_norm(flat_grad)

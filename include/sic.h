@@ -232,6 +232,22 @@ int sic_ssim_fwd_pool(const float *X, const float *Y, int planes, int H, int W, 
                       float *maps, float *x_pool, float *y_pool, void *stream);
 int sic_ssim_bwd_pool(const float *X, const float *Y, const float *maps, const float *g_ss, const float *g_cs, const float *g_pool,
                       int planes, int H, int W, float *dX, void *stream);
+/* _ex: the same kernels with (a) either image in channels-last layout - x_bands / y_bands = 0 for planar [planes, H, W], = C for a
+ * [B, H, W, C] tensor with plane = b * C + c (no conversion pass between the synthesis transform and the loss); dX has X's layout -
+ * (b) the x_hat.clamp(0, 1) of model.py:98 folded in (clamp01: X clamped as it is read, dX zero outside [0, 1]), (c) g_scale
+ * (nullable device scalar) multiplying g_ss and g_cs. */
+int sic_ssim_fwd_ex(const float *X, const float *Y, int planes, int H, int W, int x_bands, int y_bands, int clamp01, float c1, float c2,
+                    float *part_ss, float *part_cs, float *maps, float *x_pool, float *y_pool, void *stream);
+int sic_ssim_bwd_ex(const float *X, const float *Y, const float *maps, const float *g_ss, const float *g_cs, const float *g_scale,
+                    const float *g_pool, int planes, int H, int W, int x_bands, int y_bands, int clamp01, float *dX, void *stream);
+/* MS-SSIM value from the per-tile partial sums of its scales, one launch: per plane prod_{l<L-1} relu(mean cs_l)^w_l *
+ * relu(mean ss_{L-1})^w_{L-1} with w = weights (device [levels]; divided by their sum when normalize != 0, as piq does to
+ * user-supplied weights), then the mean over planes -> out (device scalar);
+ * coef (nullable, device [levels][2][planes]): d out / d mean ss_l (index 0) and / d mean cs_l (index 1), the g_ss / g_cs of
+ * sic_ssim_bwd_ex.  part: one device buffer; HOST arrays offsets[l] (float offset of scale l's part_ss; its part_cs follows at
+ * + planes * tiles[l]), tiles[l] = sic_ssim_tiles(H_l, W_l), n_valid[l] = (H_l - 10)(W_l - 10). */
+int sic_msssim_combine(const float *part, const long *offsets, const int *tiles, const long *n_valid, int levels, int planes,
+                       const float *weights, int normalize, float *out, float *coef, void *stream);
 long sic_ssim_tiles(int H, int W);
 int sic_ssim_fwd(const float *X, const float *Y, int planes, int H, int W, float c1, float c2, float *part_ss, float *part_cs,
                  float *maps, void *stream);
@@ -264,6 +280,26 @@ int sic_rans_encode(const int32_t *sym, const uint16_t *tables, const int32_t *L
                     long rows_per_stream, int stride, uint8_t *out, long cap, int32_t *out_nbytes, void *stream);
 int sic_rans_decode(const uint8_t *in, const int32_t *nbytes, const uint16_t *tables, const int32_t *Ls, int n_streams, long n,
                     long sym_per_row, long rows_per_stream, int stride, long cap, int32_t *sym, int32_t *status, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * (e)  tail of the data-parallel training step on the flat parameter / gradient buffers (trainer.py): global-norm clipping
+ * (train.py:200-202, torch.nn.utils.clip_grad_norm_) + optim.Adam (train.py:182-183), two launches (csrc/train_step.cu).
+ *   grad: the SUM over the ranks of the gradients (what the all-reduce leaves); inv_world = 1 / world size (1 on one GPU).
+ *   step: device scalar, the number of updates applied so far; incremented here (CUDA-graph capturable: no host state).
+ *   clip <= 0: no clipping.  norm_out (nullable): the pre-clip global norm of the mean gradient.  grad is not modified.
+ *   workspace: sic_clip_adam_workspace_bytes(n) bytes, 8-byte aligned. */
+/* Tail of rate_distortion_loss (model.py:75-107): R = max((sum bits_y + sum bits_z) / pixels, 0), D = 1 - *dist (similarity != 0:
+ * *dist is the MS-SSIM value) or *dist (the MSE), loss = lambda D + R; one launch forward, one backward.  bits_y [ny], bits_z [nz]:
+ * per-patch bit counts from sic_bottleneck_fwd; loss, R, D, pass: device scalars (pass = 1 where the clamp lets the gradient through,
+ * kept for the backward); bwd: g_bits_y [ny], g_bits_z [nz], g_dist (scalar) from the scalar g_loss. */
+int sic_rd_loss_fwd(const float *bits_y, int ny, const float *bits_z, int nz, const float *dist, int similarity, long pixels, float lambda,
+                    float *loss, float *R, float *D, float *pass, void *stream);
+int sic_rd_loss_bwd(const float *g_loss, const float *pass, long pixels, float lambda, int similarity, int ny, int nz, float *g_bits_y,
+                    float *g_bits_z, float *g_dist, void *stream);
+size_t sic_clip_adam_workspace_bytes(long n);
+int sic_clip_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long n, float *step, float inv_world,
+                       float clip, float lr, float beta1, float beta2, float eps, float weight_decay, float *norm_out,
+                       void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }
