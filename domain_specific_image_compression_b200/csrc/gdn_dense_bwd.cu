@@ -3,7 +3,7 @@
 //   s_i = beta_i + sum_j gamma_ij x_j^2,  d = sqrt(s)
 //   GDN :  h_i = -1/2 g_i x_i / d_i^3,  dx_j = g_j / d_j + 2 x_j sum_i gamma_ij h_i
 //   IGDN:  h_i = +1/2 g_i x_i / d_i,    dx_j = g_j d_j  + 2 x_j sum_i gamma_ij h_i
-//   d(beta_eff)_i = sum_p h_i ,  d(gamma_eff)_ij = sum_p h_i x_j^2   (the latter stays a library GEMM on the emitted h)
+//   d(beta_eff)_i = sum_p h_i ,  d(gamma_eff)_ij = sum_p h_i x_j^2   (the latter: gdn_dense_dgamma.cu, on the emitted h)
 //
 // Two launches of the same warp-specialised producer / MMA / epilogue pipeline as the forward (identical barriers, descriptors,
 // stage ring and TMEM layout; only the producer's pre-op, the orientation of gamma and the epilogue differ):
@@ -12,10 +12,9 @@
 // Algorithmic traffic: pass 1 reads x, g and writes h, direct; pass 2 reads h, x, direct and writes dx: 32 B/element, against
 // ~100 B/element for the elementwise + cuBLAS chain through torch that it replaces.
 //
-// STATUS: written after the round's GPU budget was spent — compiled for sm_100a, NOT yet run on a device.  It is therefore opt-in
-// (SIC_DENSE_BWD=1 on the Python side); the default backward remains the torch/cuBLAS path.  The forward kernel in
-// gdn_dense_ws.cu is unchanged apart from its shared declarations moving into gdn_dense_ws.cuh (the SASS of its instantiations
-// was compared equal with the build the GPU tests validated).
+// STATUS: the default backward of GDN(dense=True) since round 2 (tests/test_gpu_gdn.py: 10 shapes vs float64, the whole model with all
+// 13 sites dense); d(gamma) is the third launch, csrc/gdn_dense_dgamma.cu.  Measured: profiles/r02z_kernel_bench_dense.json,
+// profiles/r02d_ncu_kernels.txt (both passes run at 5.8 - 6.5 TB/s of DRAM traffic: the cost is the 40 B/element the three passes move).
 #include "gdn_dense_ws.cuh"
 
 namespace sic {
