@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--settle-ms", type=float, default=0.0, help="0 (default, the bench contract): exactly W warm-up steps, then K timed ones.  > 0: "
+                    "keep running untimed steps for about this long first - the sustained figure under the board's power cap (r02aw: "
+                    "SM clock 1755 MHz and 5.39 ms/step after 0.4 s of back-to-back steps, against 1875-1940 MHz and 5.14 ms in the first 0.15 s)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--dist", default="msssim", choices=["msssim", "mse"])
@@ -340,8 +343,15 @@ def run_ours(args):
 
     per_rank_ms = []
     W_, K = max(3, args.warmup), max(1, args.steps)
-    for _ in range(W_):
-        step_resident()
+    ms_warm = timed(step_resident, W_)                           # the W warm-up steps (timed only to size the settle phase below)
+    # --settle-ms > 0: keep stepping, untimed, for about that long before the timed region (the sustained, power-capped figure); the
+    # count comes from the max-over-ranks warm-up time, so every rank runs the same number of steps (each one holds collectives).
+    # The timed region is exactly K steps either way.
+    extra_warm = 0
+    if args.settle_ms > 0:
+        extra_warm = int(min(500, max(0, round(args.settle_ms / max(ms_warm / W_, 1e-3)))))
+        for _ in range(extra_warm):
+            step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -387,7 +397,7 @@ def run_ours(args):
                     "step_ms_min_median_max": [min(times), ms, max(times)]}
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms_total / K,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W_, "extra_untimed_warmup_steps": extra_warm, "ms_per_step": ms_total / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args, cfg), "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "per-step working set (>= 5 GB of activations) exceeds the 126 MB L2; no explicit flush",
