@@ -545,6 +545,32 @@ def kernel_rooflines(cfg, dev, channels_last=True, fused_first_layer=True):
         del img, y, g
     except Exception as e:
         out["conv0_gdn_fwd_tcgen05"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+    # (e) step tail: clip + Adam on flat buffers (4 B read for the norm + 16 B read / 12 B written for the update, per parameter), at
+    # the size of this model's flat buffer (L2 flushed between launches: 104 MB of state would otherwise stay resident) and at 64 M
+    # parameters (1 GB of state: larger than L2); and the whole distortion term (3 scales forward + combination, then backward)
+    try:
+        n_model = 6_270_275 if N == 128 else 14_468_163                  # live parameters of the cfg2 / cfg4 model (FlatTrainer.flat)
+        for tag, n_par, big in (("clip_adam_step_model_size", n_model, False), ("clip_adam_step_64M", 64 << 20, True)):
+            p_, g_ = torch.randn(n_par, device=dev) * 1e-2, torch.randn(n_par, device=dev) * 1e-3
+            m_, v_ = torch.zeros_like(p_), torch.zeros_like(p_)
+            st_, nrm_, ws_ = torch.zeros((), device=dev), torch.zeros((), device=dev), F.clip_adam_workspace(n_par, dev)
+            t = time_it(lambda: F.clip_adam_step(p_, g_, m_, v_, st_, nrm_, ws_, inv_world=1.0, clip=1.0, lr=1e-4, betas=(0.9, 0.999),
+                                                 eps=1e-8, weight_decay=0.0), big=big)
+            out[tag] = {"shape": [n_par], "bytes": 32 * n_par, "ms": t * 1e3, "gbs": 32 * n_par / t / 1e9,
+                        "note": "both launches (grad_sumsq_kernel + adam_clip_kernel)"}
+            del p_, g_, m_, v_
+        from domain_specific_image_compression_b200 import losses as _losses
+        xm = torch.rand(B, 3, 256, 256, device=dev).contiguous(memory_format=torch.channels_last)
+        xr = (xm + 0.1 * torch.randn_like(xm)).requires_grad_(True)
+        wm = torch.tensor([0.3, 0.5, 0.2], device=dev)
+        t = time_it(lambda: _losses.multi_scale_ssim(xr, xm, 1.0, wm, clamp01=True))
+        val = _losses.multi_scale_ssim(xr, xm, 1.0, wm, clamp01=True)
+        tb = time_it(lambda: torch.autograd.grad(val, xr, retain_graph=True))
+        out["msssim_distortion_fwd_bwd"] = {"shape": [B, 3, 256, 256], "ms_fwd": t * 1e3, "ms_bwd": tb * 1e3,
+                                            "note": "clamp + 3 scales + combination: 4 launches forward, 3 backward; latency-sized (12.6 MB images)"}
+        del xm, xr, val
+    except Exception as e:
+        out["clip_adam_step_model_size"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
     # likelihood kernel: the step's latent is tiny (launch-latency bound); the roofline figure is quoted on the top of the
     # BASELINE cfg5 sweep (128x128x320 latent, batch 16 = 84M elements, 1 GB of traffic)
     for tag, shape in (("k1_fwd_step", (B, M, 16, 16)), ("k1_fwd_sweep_top", (16, 320, 128, 128))):

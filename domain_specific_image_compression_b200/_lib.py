@@ -62,6 +62,10 @@ PROTOTYPES = {
     "sic_ssim_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     "sic_rd_loss_fwd": (_i, [_p, _i, _p, _i, _p, _i, _l, ctypes.c_float, _p, _p, _p, _p, _p]),
     "sic_rd_loss_bwd": (_i, [_p, _p, _l, ctypes.c_float, _i, _i, _i, _p, _p, _p, _p]),
+    "sic_bias_act_fwd": (_i, [_p, _p, _l, _i, _i, _p]),
+    "sic_bias_grad_workspace_bytes": (_z, [_l, _i]),
+    "sic_bias_act_bwd": (_i, [_p, _p, _l, _i, _p, _p, _p, _z, _p]),
+    "sic_pack_flat": (_i, [_p, _p, _p, _i, _p, _p]),
     "sic_clip_adam_workspace_bytes": (_z, [_l]),
     "sic_clip_adam_step": (_i, [_p, _p, _p, _p, _l, _p] + [ctypes.c_float] * 7 + [_p, _p, _z, _p]),
     "sic_quantize_indices": (_i, [_p, _i, _l, _i, _i, _p, _p, _p, _p]),

@@ -36,6 +36,7 @@ SOURCES = [
     ("msssim.cu", []),
     ("hyper_tail.cu", []),
     ("train_step.cu", []),
+    ("bias_act.cu", []),
     ("tables.cu", ["-fmad=false"]),
     ("rans_host.cpp", []),
     ("rans_device.cu", []),

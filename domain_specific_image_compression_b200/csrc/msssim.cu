@@ -238,8 +238,11 @@ __global__ void __launch_bounds__(kThreads) msssim_combine_kernel(const float *_
     }
     if (!a.normalize) wsum = 1.f;
     const float inv_planes = 1.0f / (float)a.planes;
-    float acc = 0.f;
-    for (int plane = threadIdx.x; plane < a.planes; plane += kThreads) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc = 0.f;                                             // lane 0 of each warp: sum of its planes' values
+    // one WARP per plane: the lanes fetch the tile partials side by side (a thread per plane walked up to 64 of them one after the
+    // other: 11 us of pure load latency), the xor tree gives every lane the same fixed-order sum
+    for (int plane = warp; plane < a.planes; plane += kThreads / 32) {
         float t[kMaxLevels], pw[kMaxLevels];
         float prod = 1.f;
 #pragma unroll
@@ -247,17 +250,18 @@ __global__ void __launch_bounds__(kThreads) msssim_combine_kernel(const float *_
             t[l] = 0.f;
             pw[l] = 1.f;
             if (l < L) {
-                // the last scale contributes its SSIM mean, the others their contrast-structure mean; fixed-order fold of the tiles
+                // the last scale contributes its SSIM mean, the others their contrast-structure mean
                 const float *src = part + a.off[l] + (l == L - 1 ? 0 : (long)a.planes * a.tiles[l]) + (long)plane * a.tiles[l];
                 float sum = 0.f;
-                for (int k = 0; k < a.tiles[l]; ++k) sum += __ldg(src + k);
+                for (int k = lane; k < a.tiles[l]; k += 32) sum += __ldg(src + k);
+                sum = warp_sum(sum);
                 t[l] = fmaxf(sum * a.inv_n[l], 0.f);
                 pw[l] = powf(t[l], w[l] / wsum);
                 prod *= pw[l];
             }
         }
-        acc += prod;
-        if (coef != nullptr) {
+        if (lane == 0) acc += prod;
+        if (coef != nullptr && lane == 0) {
 #pragma unroll
             for (int l = 0; l < kMaxLevels; ++l) {
                 if (l < L) {
@@ -273,8 +277,7 @@ __global__ void __launch_bounds__(kThreads) msssim_combine_kernel(const float *_
             }
         }
     }
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    if (lane == 0) red[warp] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
         float s = 0.f;

@@ -171,6 +171,65 @@ __global__ void __launch_bounds__(256) rd_loss_bwd_kernel(const float *__restric
     if (i == 0) *g_dist = similarity ? -(g * lambda) : g * lambda;
 }
 
+// ---- gradient pack: the per-parameter gradients autograd produced -> their slices of the flat gradient buffer, one launch per
+// bucket.  torch.cat of the same ~80 tensors took 50 us for 25 MB (CatArrayBatchedCopy, 1 TB/s: profiles/r02ax_ncu_launches_bench_step.txt).
+// The (pointer, offset, size) table travels in the kernel parameters, so a captured CUDA graph keeps it by value.
+constexpr int kPackMax = 128;        // tensors per launch: 128 x (8 + 8 + 4 + 4) B = 3 KB of the 4 KB parameter space
+constexpr int kPackChunk = 4096;     // floats per CTA
+struct PackArgs {
+    const float *src[kPackMax];
+    long dst_off[kPackMax];
+    int numel[kPackMax];
+    int blk_end[kPackMax];           // running total of CTAs up to and including tensor t
+    int n;
+};
+
+__global__ void __launch_bounds__(256) pack_flat_kernel(PackArgs a, float *__restrict__ dst) {
+    const int b = blockIdx.x;
+    int lo = 0, hi = a.n - 1;
+    while (lo < hi) {                // the tensor this CTA's chunk belongs to: first t with blk_end[t] > b
+        const int mid = (lo + hi) >> 1;
+        if (a.blk_end[mid] > b) hi = mid;
+        else lo = mid + 1;
+    }
+    const int first = lo ? a.blk_end[lo - 1] : 0;
+    const long e0 = (long)(b - first) * kPackChunk;
+    const int left = a.numel[lo] - (int)e0;
+    const int cnt = left < kPackChunk ? left : kPackChunk;
+    const float *s = a.src[lo] + e0;
+    float *d = dst + a.dst_off[lo] + e0;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+        const int c4 = cnt >> 2;
+        const float4 *s4 = reinterpret_cast<const float4 *>(s);
+        float4 *d4 = reinterpret_cast<float4 *>(d);
+        float4 v[kPackChunk / 4 / 256];
+#pragma unroll
+        for (int u = 0; u < kPackChunk / 4 / 256; ++u) {
+            const int i = threadIdx.x + u * 256;
+            if (i < c4) v[u] = ldg_stream(s4 + i);
+        }
+#pragma unroll
+        for (int u = 0; u < kPackChunk / 4 / 256; ++u) {
+            const int i = threadIdx.x + u * 256;
+            if (i < c4) d4[i] = v[u];        // default caching: the all-reduce / the norm kernel read it next
+        }
+        for (int i = (c4 << 2) + threadIdx.x; i < cnt; i += 256) d[i] = __ldg(s + i);
+    } else {                         // a slice that starts off a 16-byte boundary (an odd-sized tensor came before it)
+        float v[kPackChunk / 256];
+#pragma unroll
+        for (int u = 0; u < kPackChunk / 256; ++u) {
+            const int i = threadIdx.x + u * 256;
+            if (i < cnt) v[u] = __ldg(s + i);
+        }
+#pragma unroll
+        for (int u = 0; u < kPackChunk / 256; ++u) {
+            const int i = threadIdx.x + u * 256;
+            if (i < cnt) d[i] = v[u];
+        }
+    }
+}
+
+SIC_REGISTER_KERNEL("pack_flat_kernel", pack_flat_kernel);
 SIC_REGISTER_KERNEL("grad_sumsq_kernel", grad_sumsq_kernel);
 SIC_REGISTER_KERNEL("adam_clip_kernel", adam_clip_kernel);
 
@@ -225,5 +284,30 @@ extern "C" int sic_rd_loss_bwd(const float *g_loss, const float *pass, long pixe
     rd_loss_bwd_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g_loss, pass, (float)pixels, lambda, similarity != 0, ny, nz, g_bits_y,
                                                                           g_bits_z, g_dist);
     SIC_CHECK_LAUNCH("sic_rd_loss_bwd");
+    return 0;
+}
+
+extern "C" int sic_pack_flat(const float *const *srcs, const long *numels, const long *dst_offsets, int n, float *dst, void *stream) {
+    SIC_CHECK_ARG(n > 0 && srcs && numels && dst_offsets && dst, "sic_pack_flat: nothing to pack or null pointer (n=%d)", n);
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int t0 = 0; t0 < n; t0 += kPackMax) {
+        PackArgs a;
+        a.n = n - t0 < kPackMax ? n - t0 : kPackMax;
+        long blocks = 0;
+        for (int t = 0; t < a.n; ++t) {
+            const long ne = numels[t0 + t];
+            SIC_CHECK_ARG(srcs[t0 + t] && ne > 0 && ne < (1L << 31) && dst_offsets[t0 + t] >= 0 && (((uintptr_t)srcs[t0 + t]) & 3) == 0,
+                          "sic_pack_flat: tensor %d: null / empty / >= 2^31 elements / negative offset", t0 + t);
+            a.src[t] = srcs[t0 + t];
+            a.dst_off[t] = dst_offsets[t0 + t];
+            a.numel[t] = (int)ne;
+            blocks += (ne + kPackChunk - 1) / kPackChunk;
+            SIC_CHECK_ARG(blocks < (1L << 31), "sic_pack_flat: too many chunks");
+            a.blk_end[t] = (int)blocks;
+        }
+        for (int t = a.n; t < kPackMax; ++t) { a.src[t] = nullptr; a.dst_off[t] = 0; a.numel[t] = 0; a.blk_end[t] = (int)blocks; }
+        pack_flat_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, dst);
+        SIC_CHECK_LAUNCH("sic_pack_flat");
+    }
     return 0;
 }

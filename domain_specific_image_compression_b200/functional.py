@@ -455,7 +455,7 @@ class _Col2ImRGB(torch.autograd.Function):
             dD = torch.empty((B, 80, H, W), dtype=torch.float32, device=g.device, memory_format=torch.channels_last)
             with torch.cuda.device(g.device):
                 _launch(lib.sic_deconv_rgb_im2col(_ptr(g), B, H, W, _ptr(dD), _stream()), "sic_deconv_rgb_im2col")
-        dbias = g.sum(dim=(0, 2, 3)) if (has_bias and ctx.needs_input_grad[1]) else None
+        dbias = channel_sum(g) if (has_bias and ctx.needs_input_grad[1]) else None
         return dD, dbias
 
 
@@ -854,3 +854,99 @@ def rd_loss_tail(bits_y: torch.Tensor, bits_z: torch.Tensor, dist: torch.Tensor,
     `similarity`, else the MSE): R = max((sum bits_y + sum bits_z) / pixels, 0), D = 1 - dist | dist, loss = lambda D + R.
     One launch forward, one backward; R and D carry no gradient (the reference returns them detached)."""
     return _RDLossTail.apply(bits_y, bits_z, dist, int(pixels), float(lambda_rd), bool(similarity))
+
+
+def pack_flat(tensors, dst_offsets, dst: torch.Tensor) -> None:
+    """Copy every (flat, contiguous, CUDA float32) tensor of `tensors` to dst[dst_offsets[t] : dst_offsets[t] + numel] in one launch per
+    128 tensors (the gradient pack of FlatTrainer; replaces torch.cat(..., out=slice))."""
+    global launch_count
+    lib = _lib.load()
+    n = len(tensors)
+    if n == 0:
+        return
+    for t, off in zip(tensors, dst_offsets):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == dst.device):
+            raise _lib.SicError("pack_flat: expected contiguous CUDA float32 tensors on the destination's device")
+        if off < 0 or off + t.numel() > dst.numel():
+            raise _lib.SicError(f"pack_flat: slice [{off}, {off + t.numel()}) outside the destination of {dst.numel()} elements")
+    srcs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    numels = (ctypes.c_long * n)(*[t.numel() for t in tensors])
+    offs = (ctypes.c_long * n)(*[int(o) for o in dst_offsets])
+    with torch.cuda.device(dst.device):
+        _launch(lib.sic_pack_flat(srcs, numels, offs, n, _ptr(dst), _stream()), "sic_pack_flat")
+    launch_count += (n - 1) // 128
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# bias add (+ ReLU) after a bias-free convolution, channels-last activations
+class _BiasAct(torch.autograd.Function):
+    @staticmethod
+    @_amp_fwd
+    def forward(ctx, t, bias, relu: bool):
+        lib = _lib.load()
+        bias = _require_cuda_f32(bias, "bias")
+        B, C, H, W = t.shape
+        with torch.cuda.device(t.device):
+            _launch(lib.sic_bias_act_fwd(_ptr(t), _ptr(bias), B * H * W, C, int(relu), _stream()), "sic_bias_act_fwd")
+        ctx.mark_dirty(t)
+        ctx.relu = bool(relu)
+        if relu:
+            ctx.save_for_backward(t)
+        return t
+
+    @staticmethod
+    @_amp_bwd
+    def backward(ctx, g):
+        global launch_count
+        lib = _lib.load()
+        g = _require_cuda_f32_cl(g, "grad_output")
+        B, C, H, W = g.shape
+        P = B * H * W
+        y = ctx.saved_tensors[0] if ctx.relu else None
+        dt = torch.empty_like(g) if ctx.relu else None
+        dbias = torch.empty(C, dtype=torch.float32, device=g.device)
+        ws = _workspace(g.device, int(lib.sic_bias_grad_workspace_bytes(P, C)), kind="bias_grad")
+        with torch.cuda.device(g.device):
+            _launch(lib.sic_bias_act_bwd(_ptr(g), _ptr(y), P, C, _ptr(dt), _ptr(dbias), _ptr(ws), ws.numel(), _stream()), "sic_bias_act_bwd")
+        launch_count += 1
+        return (dt if ctx.relu else g), dbias, None
+
+
+def _is_channels_last_dense(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _require_cuda_f32_cl(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.float32 or t.dim() != 4:
+        raise _lib.SicError(f"{name}: expected a 4-D CUDA float32 tensor")
+    return t if _is_channels_last_dense(t) else t.contiguous(memory_format=torch.channels_last)
+
+
+def bias_act_supported(t: torch.Tensor, bias: Optional[torch.Tensor]) -> bool:
+    """True when bias_act can take `t` as it is: a dense channels-last CUDA float32 activation with a float32 bias of at most 1024 channels."""
+    return (bias is not None and isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and bias.dtype == torch.float32
+            and _is_channels_last_dense(t) and t.shape[1] <= 1024 and t.numel() > 0)
+
+
+def bias_act(t: torch.Tensor, bias: torch.Tensor, relu: bool = False) -> torch.Tensor:
+    """t + bias[None, :, None, None] (then ReLU) IN PLACE on the channels-last output `t` of a bias-free convolution - PyTorch's own
+    add_(bias) / relu_ in one launch, same values - with d(bias) (and the ReLU mask) of the backward as one pass + a fold instead of
+    threshold_backward + a reduction over (B, H, W).  See bias_act_supported()."""
+    if not bias_act_supported(t, bias):
+        raise _lib.SicError("bias_act: expects a dense channels-last CUDA float32 activation and a float32 bias (no CPU path)")
+    return _BiasAct.apply(t, bias, bool(relu))
+
+
+def channel_sum(g: torch.Tensor) -> torch.Tensor:
+    """sum over (B, H, W) of a channels-last [B,C,H,W] CUDA float32 tensor -> [C], deterministic (the d(bias) reduction)."""
+    global launch_count
+    lib = _lib.load()
+    g = _require_cuda_f32_cl(g, "g")
+    B, C, H, W = g.shape
+    P = B * H * W
+    out = torch.empty(C, dtype=torch.float32, device=g.device)
+    ws = _workspace(g.device, int(lib.sic_bias_grad_workspace_bytes(P, C)), kind="bias_grad")
+    with torch.cuda.device(g.device):
+        _launch(lib.sic_bias_act_bwd(_ptr(g), None, P, C, None, _ptr(out), _ptr(ws), ws.numel(), _stream()), "sic_bias_act_bwd")
+    launch_count += 1
+    return out

@@ -37,6 +37,7 @@ class GDN(nn.Module):
 
 
 FUSE_CONV_BIAS = True      # fold each convolution's bias add (and its gradient reduction) into the following GDN kernel
+FUSE_BIAS_ACT = True       # channels-last activations: bias add (+ the ReLU that follows) of the other convolutions as one in-place launch
 
 
 # Opt-in (bench.py switches it on; a training script does the same with `layers.FUSE_FIRST_LAYER = True`): in TRAINING mode run conv 3->N 3x3 + bias + GDN of g_a as ONE kernel
@@ -120,6 +121,23 @@ def _run(seq: nn.Sequential, x):
                 x = t if bias is None else t + bias.view(1, -1, 1, 1)
                 i += 1
             continue
+        if (FUSE_BIAS_ACT and m.__class__ in (nn.Conv2d, nn.ConvTranspose2d) and m.bias is not None and x.is_cuda
+                and x.dtype == torch.float32 and F_sic._is_channels_last_dense(x) and not torch.is_autocast_enabled()
+                and not (isinstance(nxt, GDN) and not nxt.dense and FUSE_CONV_BIAS)):
+            # a biased convolution that no diagonal GDN follows (hyper transforms: conv -> ReLU; the last analysis convolution): bias-free
+            # cuDNN convolution, then bias (+ ReLU) in place in one launch; d(bias) and the ReLU mask in one pass in the backward
+            if isinstance(m, nn.Conv2d):
+                t = F.conv2d(x, m.weight, None, m.stride, m.padding, m.dilation, m.groups)
+            else:
+                t = F.conv_transpose2d(x, m.weight, None, m.stride, m.padding, m.output_padding, m.groups, m.dilation)
+            if F_sic.bias_act_supported(t, m.bias):
+                relu = isinstance(nxt, nn.ReLU)
+                x = F_sic.bias_act(t, m.bias, relu=relu)
+                i += 2 if relu else 1
+            else:                                     # NCHW activations: PyTorch's own add (same values)
+                x = t + m.bias.view(1, -1, 1, 1)
+                i += 1
+            continue
         if (FUSE_CONV_BIAS and isinstance(nxt, GDN) and not nxt.dense and m.__class__ in (nn.Conv2d, nn.ConvTranspose2d)
                 and m.bias is not None and x.is_cuda):
             if isinstance(m, nn.Conv2d):
@@ -198,7 +216,7 @@ class HyperAnalysis(nn.Module):
         self.h_a = _stack([("c", M, N, 3, 1), ("r",), ("c", N, N, 3, 1), ("r",), ("c", N, N, 5, 2), ("r",), ("c", N, N, 5, 2)])
 
     def forward(self, y):
-        return self.h_a(y)
+        return _run(self.h_a, y)
 
 
 class HyperSynthesis(nn.Module):
@@ -219,8 +237,12 @@ class HyperSynthesis(nn.Module):
             self.mlp_sigma = nn.Sequential(nn.Conv2d(N, N, 1), nn.ReLU(), nn.Conv2d(N, M, 1))
             self.mlp_nu = nn.Sequential(nn.Conv2d(N, N, 1), nn.ReLU(), nn.Conv2d(N, M, 1))
 
+    def trunk(self, z):
+        """h_s proper: deconv -> ReLU -> deconv -> ReLU (layers.py:122-127)."""
+        return _run(self.h_s, z)
+
     def forward(self, z):
-        t = self.h_s(z)
+        t = self.trunk(z)
         if self.spatial_params:
             return self.to_sigma(t), self.to_nu(t)
         p = self.pool(t)

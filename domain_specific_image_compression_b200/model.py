@@ -84,7 +84,7 @@ class CompressionModel(nn.Module):
             # N4: pool -> two MLPs -> exp / clamp as ONE kernel with a fixed, batch-size-independent summation order (the eager
             # chain is ~15 launches, and its cuDNN/cuBLAS GEMMs may round differently at different batch sizes, which would
             # desynchronise encoder and decoder tables)
-            t = self.h_s.h_s(z_tilde)
+            t = self.h_s.trunk(z_tilde)
             sigma_k, nu_k = F_sic.hyper_tail(t, self.h_s.mlp_sigma, self.h_s.mlp_nu, self.min_nu, self.max_nu)
             return sigma_k, nu_k, sigma_k.expand_as(like), nu_k.expand_as(like)
         log_sigma, log_nu = self.h_s(z_tilde)

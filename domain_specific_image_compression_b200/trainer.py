@@ -85,6 +85,7 @@ class FlatTrainer:
             p.data = view
             offsets.append(off)
             off += n
+        self._offsets = offsets
         self.flat.requires_grad_(True)
         self.flat_grad = torch.zeros_like(self.flat)              # persistent: what the all-reduces and Adam work on
         if self.world > 1:                     # identical replicas: rank 0's weights win
@@ -155,7 +156,14 @@ class FlatTrainer:
             for st in (self._main_stream, _side_streams.get(self.flat_grad.device.index)):
                 if st is not None and st != cur and (not capturing or _is_capturing(st)):
                     cur.wait_stream(st)
-        torch.cat([_flat_in_param_order(self.live[i].grad, self.live[i]) for i in range(a, b)], out=self.flat_grad[lo:hi])
+        grads = [_flat_in_param_order(self.live[i].grad, self.live[i]) for i in range(a, b)]
+        if self.flat_grad.is_cuda and self.fused:
+            from . import functional as F_sic
+            keep = [g for g in grads if g.numel() > 0]
+            F_sic.pack_flat([g.contiguous() for g in keep], [self._offsets[i] for i, g in zip(range(a, b), grads) if g.numel() > 0],
+                            self.flat_grad)
+        else:
+            torch.cat(grads, out=self.flat_grad[lo:hi])
         self.fire_order.append(k)
         if self.world > 1 and not _DIAG_NO_ALLREDUCE:   # asynchronous: runs on the collective's own stream under the rest of backward()
             self._works.append(dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))

@@ -296,6 +296,19 @@ int sic_rd_loss_fwd(const float *bits_y, int ny, const float *bits_z, int nz, co
                     float *loss, float *R, float *D, float *pass, void *stream);
 int sic_rd_loss_bwd(const float *g_loss, const float *pass, long pixels, float lambda, int similarity, int ny, int nz, float *g_bits_y,
                     float *g_bits_z, float *g_dist, void *stream);
+/* Bias add (+ ReLU) after a bias-free cuDNN convolution, and its adjoint, on position-major activations [P, C] (channels-last,
+ * P = B*H*W); csrc/bias_act.cu.  Replaces PyTorch's add_(bias) / relu_ and, in the backward, threshold_backward + the sum over
+ * (B, H, W) for d(bias) (layers.py:104-139 hyper transforms, :73 last analysis convolution; also d(bias) of the last synthesis layer).
+ *   fwd: t = act(t + bias) IN PLACE; relu != 0: act = ReLU as `v < 0 ? 0 : v`.  Same fp32 values as PyTorch's two ops.
+ *   bwd: y / dt NULL: d(bias)[c] = sum_p g[p, c].  Else y = the forward's output: dt = g where y > 0 else 0, d(bias) = sum_p dt.
+ *        Deterministic (fixed-order partial sums).  workspace: sic_bias_grad_workspace_bytes(P, C) bytes. */
+int sic_bias_act_fwd(float *t, const float *bias, long P, int C, int relu, void *stream);
+size_t sic_bias_grad_workspace_bytes(long P, int C);
+int sic_bias_act_bwd(const float *g, const float *y, long P, int C, float *dt, float *dbias, void *workspace, size_t workspace_bytes,
+                     void *stream);
+/* Gradient pack of trainer.FlatTrainer: n device tensors (HOST arrays: srcs[t] device pointer, numels[t], dst_offsets[t] in floats)
+ * copied to dst + dst_offsets[t], one launch per 128 tensors; the table is passed by value (graph-capturable). */
+int sic_pack_flat(const float *const *srcs, const long *numels, const long *dst_offsets, int n, float *dst, void *stream);
 size_t sic_clip_adam_workspace_bytes(long n);
 int sic_clip_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, long n, float *step, float inv_world,
                        float clip, float lr, float beta1, float beta2, float eps, float weight_decay, float *norm_out,

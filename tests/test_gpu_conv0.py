@@ -137,8 +137,9 @@ def test_model_training_step_with_fused_first_layer():
     x = torch.rand(2, 3, 64, 80, device="cuda")
     ny, nz = torch.rand(2, 48, 4, 5, device="cuda") - 0.5, torch.rand(2, 32, 1, 2, device="cuda") - 0.5
     res = {}
-    old_tf32 = torch.backends.cudnn.allow_tf32
+    old_tf32, old_ba = torch.backends.cudnn.allow_tf32, L.FUSE_BIAS_ACT
     torch.backends.cudnn.allow_tf32 = False
+    L.FUSE_BIAS_ACT = False          # the fused layer hands on channels-last activations, where the bias kernels would add launches of their own
     try:
         for fused in (False, True):
             L.FUSE_FIRST_LAYER = fused
@@ -158,6 +159,7 @@ def test_model_training_step_with_fused_first_layer():
         assert torch.equal(e_on, e_off)
     finally:
         L.FUSE_FIRST_LAYER = False
+        L.FUSE_BIAS_ACT = old_ba
         torch.backends.cudnn.allow_tf32 = old_tf32
     (l0, g0, y0, n0), (l1, g1, y1, n1) = res[False], res[True]
     assert n1 == n0                                               # our launch count is unchanged (1 fwd + 2 bwd either way); two cuDNN launches disappear

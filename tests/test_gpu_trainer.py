@@ -66,6 +66,30 @@ def test_clip_adam_step_rejects_bad_arguments():
         F.clip_adam_step(p, p.clone(), p.clone(), p.clone(), step, None, ws, **{**kw, "betas": (1.0, 0.999)})
 
 
+def test_pack_flat_equals_cat():
+    """The gradient pack: 300 tensors of odd and large sizes (slices off the 16-byte grid, several launches of 128, chunks of 4096
+    floats with ragged ends) land where torch.cat puts them; untouched gaps stay untouched."""
+    from domain_specific_image_compression_b200 import _lib
+    from domain_specific_image_compression_b200 import functional as F
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    sizes = [1, 3, 4, 5, 4096, 4097, 8191, 100_003, 1_000_000] + [int(v) for v in torch.randint(1, 20_000, (291,), generator=torch.Generator().manual_seed(1))]
+    ts = [torch.randn(n, device="cuda", generator=gen) for n in sizes]
+    offs, off = [], 7                                            # start off the grid on purpose, leave a gap of 2 between tensors
+    for n in sizes:
+        offs.append(off)
+        off += n + 2
+    dst = torch.full((off + 5,), -7.0, device="cuda")
+    F.pack_flat(ts, offs, dst)
+    ref = torch.full_like(dst, -7.0)
+    for t, o in zip(ts, offs):
+        ref[o:o + t.numel()] = t
+    assert torch.equal(dst, ref)
+    with pytest.raises(_lib.SicError):
+        F.pack_flat([ts[0]], [dst.numel()], dst)                 # slice outside the destination
+    with pytest.raises(_lib.SicError):
+        F.pack_flat([ts[0].cpu()], [0], dst)
+
+
 class Toy(torch.nn.Module):
     def __init__(self):
         super().__init__()
