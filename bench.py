@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--e2e-idle-s", type=float, default=1.0, help="idle time between the device-resident measurement and the end-to-end one "
+                    "(both then start from an idle device, W warm-up steps, K timed steps)")
     ap.add_argument("--settle-ms", type=float, default=0.0, help="0 (default, the bench contract): exactly W warm-up steps, then K timed ones.  > 0: "
                     "keep running untimed steps for about this long first - the sustained figure under the board's power cap (r02aw: "
                     "SM clock 1755 MHz and 5.39 ms/step after 0.4 s of back-to-back steps, against 1875-1940 MHz and 5.14 ms in the first 0.15 s)")
@@ -180,43 +182,109 @@ def workload_name(args, cfg):
 
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
+
+    In-process NVML (pynvml), polled every 10 ms by a thread that is started BEFORE the warm-up steps: the round's earlier version
+    spawned `nvidia-smi -lms 100` at the start of the timed region, and that process's NVML initialisation (it enumerates every GPU of
+    the box) stalled work submission for a few ms of a 100 ms region - the device-resident loop measured 3-6 % slower than the
+    end-to-end loop timed right after it (r02ay: 5.14 vs 4.89 ms, r02ba: 5.25 vs 4.95 ms).  Only samples stamped inside
+    [mark_begin, mark_end] are reported.  Falls back to the nvidia-smi process (also started early) when pynvml is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.handle = index, [], None, None, None
+        self.t0 = self.t1 = None
+        self._stop = threading.Event()
+        self.thread = None
+
+    def _open_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        handle = None
+        try:                                                     # the CUDA device may be remapped (CUDA_VISIBLE_DEVICES): go by UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.nvml, self.handle = pynvml, handle
+        self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        get = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {}
+        for name, a, b in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+                           ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+                           ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap")):
+            bits[name] = getattr(pynvml, a, None) or getattr(pynvml, b)
+        self._get_reasons, self._bits = get, bits
+
+    def _poll_nvml(self):
+        nv, h = self.nvml, self.handle
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(self._get_reasons(h))
+                self.rows.append((time.perf_counter(), sm, self.max_sm, [n for n, b in self._bits.items() if mask & b]))
+            except Exception:
+                pass
+            self._stop.wait(0.010)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.rows.append((time.perf_counter(), float(r[0]), float(r[1]),
+                                  [n for n, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")]))
+            except (ValueError, IndexError):
+                continue
 
     def start(self):
         try:
+            self._open_nvml()
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            self.source = "nvml in-process, 10 ms period"
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read_smi, daemon=True).start()
+            self.source = "nvidia-smi -lms 50"
         except OSError:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if self.proc is not None:
+            time.sleep(0.1)
+            self.proc.terminate()
+        rows = list(self.rows)
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        note = None
+        if not inside and rows and self.t0 is not None:          # a region shorter than the sampling period: the nearest sample
+            mid = 0.5 * (self.t0 + (self.t1 or self.t0))
+            inside, note = [min(rows, key=lambda r: abs(r[0] - mid))], "no sample fell inside the timed region: nearest one reported"
+        sm = sorted(r[1] for r in inside)
+        reasons = sorted({n for r in inside for n in r[3]})
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+               "reasons": reasons, "samples": len(sm), "source": self.source}
+        if note:
+            out["note"] = note
+        return out
 
 
 def run_ours(args):
@@ -343,6 +411,9 @@ def run_ours(args):
 
     per_rank_ms = []
     W_, K = max(3, args.warmup), max(1, args.steps)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                          # before the warm-up: NVML initialisation stays out of the timed region
     ms_warm = timed(step_resident, W_)                           # the W warm-up steps (timed only to size the settle phase below)
     # --settle-ms > 0: keep stepping, untimed, for about that long before the timed region (the sustained, power-capped figure); the
     # count comes from the max-over-ranks warm-up time, so every rank runs the same number of steps (each one holds collectives).
@@ -352,16 +423,19 @@ def run_ours(args):
         extra_warm = int(min(500, max(0, round(args.settle_ms / max(ms_warm / W_, 1e-3)))))
         for _ in range(extra_warm):
             step_resident()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = F_sic.launch_count
     torch.cuda.profiler.start()                              # ncu --profile-from-start off isolates the timed region (all threads)
+    sampler.mark_begin()
     ms_total = timed(step_resident, K)
+    sampler.mark_end()
     torch.cuda.profiler.stop()
     launches = F_sic.launch_count - l0 if run_static is None else launches_per_step * K
     clocks = sampler.stop() if rank == 0 else None
-    for _ in range(2):
+    # The end-to-end loop is measured under the protocol of the device-resident one: from an idle device (the board's power governor
+    # averages over ~1 s: straight after 25 back-to-back steps the SM clock is already capped, r02aw / r02bb), W warm-up steps, K timed.
+    barrier()
+    time.sleep(args.e2e_idle_s)
+    for _ in range(W_):
         step_e2e()
 
     def timed_e2e(steps):
@@ -407,7 +481,7 @@ def run_ours(args):
                        "gradient_buckets": [hi - lo for lo, hi, _, _ in trainer.buckets] if world > 1 else None,
                        "cudnn_benchmark": not args.no_cudnn_benchmark, "cudnn_benchmark_limit": torch.backends.cudnn.benchmark_limit},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
-                    "ms_per_step": ms_e2e / K, "last_loss": e2e_losses[-1],
+                    "ms_per_step": ms_e2e / K, "last_loss": e2e_losses[-1], "protocol": f"{args.e2e_idle_s} s idle, {W_} warm-up steps, {K} timed",
                     "how": "HostFedLoop: pinned batch -> copy stream -> landing buffer -> static input; loss -> pinned host, read one step late"},
             "gpu_launches": launches, "per_rank_ms_per_step": per_rank_ms or None, "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base,
             "gpu_eager_baseline": gpu_eager,
