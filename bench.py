@@ -411,6 +411,9 @@ def run_ours(args):
 
     per_rank_ms = []
     W_, K = max(3, args.warmup), max(1, args.steps)
+    if os.environ.get("SIC_BENCH_START_AT"):                     # diagnosis only (scripts/gpu_duo.sh): independent processes on different
+        torch.cuda.synchronize()                                 # GPUs of one box start their warm-up at the same wall-clock time
+        time.sleep(max(0.0, float(os.environ["SIC_BENCH_START_AT"]) - time.time()))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                                          # before the warm-up: NVML initialisation stays out of the timed region
