@@ -481,6 +481,7 @@ def run_ours(args):
                        "conv_math": "cuDNN fp32 with TF32 allowed (PyTorch default, as the reference)",
                        "activation_layout": "NCHW" if args.nchw else "channels_last", "launch": graph_note,
                        "rgb_channel_padding": args.pad_rgb, "gdn": args.gdn, "fused_first_layer": bool(_layers.FUSE_FIRST_LAYER), "gemm_last_layer": bool(_layers.FAST_LAST_LAYER), "hyper_branch_on_side_stream": bool(_model.OVERLAP_HYPER_BRANCH),
+                       "step_tail": "MS-SSIM scales + combination + clamp, loss tail, bias + ReLU, gradient pack, clip + Adam as sic kernels (DESIGN 5e)" if trainer.fused else "torch ops",
                        "gradient_buckets": [hi - lo for lo, hi, _, _ in trainer.buckets] if world > 1 else None,
                        "cudnn_benchmark": not args.no_cudnn_benchmark, "cudnn_benchmark_limit": torch.backends.cudnn.benchmark_limit},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world, "d2h_bytes_per_step": 4 * world,
