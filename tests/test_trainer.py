@@ -68,6 +68,21 @@ def test_buckets_partition_the_flat_buffer_and_fire_in_backward_order():
     assert sorted(small.fire_order) == [0, 1, 2, 3]
 
 
+def test_default_bucketing_and_optimizer_choice_on_the_host():
+    """One process has nothing to overlap: the default is ONE bucket (one pack at the end of backward()); the 6 MB buckets are the
+    default only with a process group of more than one rank (exercised by the gloo test below).  On CPU tensors the trainer keeps
+    torch.optim.Adam; the fused clip + Adam kernels are a GPU-only path that refuses host buffers instead of falling back."""
+    from domain_specific_image_compression_b200 import SicError
+    m = Toy()
+    tr = FlatTrainer(m, exclude=["gamma"])
+    assert len(tr.buckets) == 1 and tr.buckets[0][:2] == (0, tr.flat.numel())
+    assert not tr.fused and tr.opt is not None
+    m2 = Toy()
+    forced = FlatTrainer(m2, exclude=["gamma"], fused=True)
+    with pytest.raises(SicError):
+        forced.step(lambda: _loss(m2, torch.rand(2, 3, 8, 8)))
+
+
 def test_dead_parameters_follow_the_gdn_mode():
     """Per GDN site: the reference's diagonal path trains `gamma_conv.weight` and never touches the CxC `gamma` (layers.py:13,21);
     GDN(dense=True) trains `gamma` and never touches `gamma_conv.weight`.  The bucket must hold exactly the live ones."""
