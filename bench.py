@@ -17,6 +17,9 @@ one flat-bucket NCCL all-reduce per step for N > 1.  Prints ONE JSON line (rank 
             the GPU box; the port is pinned bit-for-bit against the imported reference by tests/test_oracle_golden.py) on
             the host cores, bounded sample, median step
   gpu_eager_baseline  the same eager op chains on THIS GPU (fp32, NCHW, same cuDNN flags): the bar the fused kernels must beat
+  clocks    SM clock (median) and throttle reasons of the samples stamped INSIDE the timed region, from an in-process NVML thread
+            (10 ms period) started before the warm-up; `value` and `e2e` are each timed as W warm-up steps + K steps from an idle
+            device (--e2e-idle-s between them); --settle-ms gives the sustained, power-capped figure instead of the first 0.1 s
 --impl reference: only the CPU arm (rank 0), same metric/config/unit, the caller's --steps/--warmup honoured.
 """
 from __future__ import annotations
