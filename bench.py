@@ -715,7 +715,7 @@ def kernel_rooflines(cfg, dev, channels_last=True, fused_first_layer=True):
     if channels_last and fused_first_layer:
         dom, kid = out["gdn_bwd_nhwc_kernel_alone_128"], "gdn_bwd_nhwc_kernel<0>"
         kname = ("gdn_bwd_nhwc_kernel (GDN/IGDN backward, channels_last; 12 launches and the largest share of the step among our kernels: "
-                 "profiles/r02v_ncu_launches_bench_step.txt) at its largest site in the step, 128^2 (the 256^2 site is inside the fused "
+                 "profiles/r02ax_ncu_launches_bench_step.txt) at its largest site in the step, 128^2 (the 256^2 site is inside the fused "
                  "first-layer kernel; this kernel at 256^2: kernels.gdn_bwd_channels_last)")
     elif channels_last:
         dom, kid = out["gdn_bwd_channels_last"], "gdn_bwd_nhwc_kernel<0>"
